@@ -1,0 +1,109 @@
+// extern "C" surface of libaf3b200.so (declared in include/af3b200.h).  Plain pointers and sizes only.
+#include "../../include/af3b200.h"
+
+#include "common.h"
+
+namespace af3 {
+const char* last_error_cstr();
+int gemm_bf16(cudaStream_t stream, const bf16* x, int ldx, const bf16* w, int ldw, void* out, int ldo, int n_tok,
+              int n_feat, int K, int flags, const bf16* bias, const bf16* resid, int ld_res, int res_period);
+int logmel(cudaStream_t stream, const float* wave, int n_win, int n_samples, const float* hann, const float* table,
+           const float* filt, const int* klo, const int* khi, float* out, int* win_max);
+int layernorm(cudaStream_t, const bf16*, bf16*, const bf16*, const bf16*, int, int, float);
+int avgpool_layernorm(cudaStream_t, const bf16*, bf16*, const bf16*, const bf16*, int, int, int, float);
+int rmsnorm(cudaStream_t, const bf16*, bf16*, const bf16*, int, int, float, const int*);
+int im2col_conv1(cudaStream_t, const void*, int, bf16*, int, int, int);
+int im2col_conv2(cudaStream_t, const bf16*, bf16*, int, int, int);
+int pack_gate_up(cudaStream_t, const bf16*, const bf16*, bf16*, int, int);
+int rope_kv_append(cudaStream_t, bf16*, bf16*, bf16*, int, int, int, int, int, int, int, const int*, const int*,
+                   const float*);
+int embed_scatter(cudaStream_t, const int64_t*, int, const bf16*, int, int64_t, const bf16*, int, int, const int*, bf16*,
+                  int*, int*);
+int argmax(cudaStream_t, const float*, int, int, int64_t*);
+int attention(cudaStream_t stream, const bf16* q, int ldq, const bf16* k, const bf16* v, int ldk, int kv_layout,
+              int Tk_pitch, bf16* out, int ldo, int B, int H, int Hkv, int D, int Tq, int Tk, float scale, int causal,
+              const int* kv_len, const int* kv_start);
+size_t decode_attention_scratch_bytes(int B, int H, int D);
+int decode_attention(cudaStream_t stream, const bf16* qkv, const bf16* k_cache, const bf16* v_cache, bf16* out,
+                     float* scratch, int B, int H, int Hkv, int D, int Tmax, const int* ctx_len, const int* kv_start,
+                     float scale);
+}  // namespace af3
+
+using af3::bf16;
+#define S(stream) reinterpret_cast<cudaStream_t>(stream)
+#define B16(p) reinterpret_cast<const bf16*>(p)
+#define B16M(p) reinterpret_cast<bf16*>(p)
+
+extern "C" {
+
+const char* af3_last_error(void) { return af3::last_error_cstr(); }
+int af3_abi_version(void) { return 1; }
+
+int af3_gemm_bf16(void* stream, const void* x, int ldx, const void* w, int ldw, void* out, int ldo, int n_tok, int n_feat,
+                  int K, int flags, const void* bias, const void* resid, int ld_res, int res_period) {
+    return af3::gemm_bf16(S(stream), B16(x), ldx, B16(w), ldw, out, ldo, n_tok, n_feat, K, flags, B16(bias), B16(resid),
+                          ld_res, res_period);
+}
+
+int af3_pack_gate_up(void* stream, const void* gate, const void* up, void* packed, int F, int K) {
+    return af3::pack_gate_up(S(stream), B16(gate), B16(up), B16M(packed), F, K);
+}
+
+int af3_logmel(void* stream, const float* wave, int n_win, int n_samples, const float* hann, const float* dft_table,
+               const float* mel_filters, const int* mel_klo, const int* mel_khi, float* out, int* scratch_max) {
+    return af3::logmel(S(stream), wave, n_win, n_samples, hann, dft_table, mel_filters, mel_klo, mel_khi, out,
+                       scratch_max);
+}
+
+int af3_im2col_conv1(void* stream, const void* in, int in_is_f32, void* cols, int n_win, int C, int T) {
+    return af3::im2col_conv1(S(stream), in, in_is_f32, B16M(cols), n_win, C, T);
+}
+int af3_im2col_conv2(void* stream, const void* in, void* cols, int n_win, int C, int T) {
+    return af3::im2col_conv2(S(stream), B16(in), B16M(cols), n_win, C, T);
+}
+
+int af3_layernorm(void* stream, const void* x, void* y, const void* gamma, const void* beta, int rows, int dim, float eps) {
+    return af3::layernorm(S(stream), B16(x), B16M(y), B16(gamma), B16(beta), rows, dim, eps);
+}
+int af3_avgpool_layernorm(void* stream, const void* x, void* y, const void* gamma, const void* beta, int n_win, int T,
+                          int dim, float eps) {
+    return af3::avgpool_layernorm(S(stream), B16(x), B16M(y), B16(gamma), B16(beta), n_win, T, dim, eps);
+}
+int af3_rmsnorm(void* stream, const void* x, void* y, const void* weight, int rows, int dim, float eps,
+                const int* row_idx) {
+    return af3::rmsnorm(S(stream), B16(x), B16M(y), B16(weight), rows, dim, eps, row_idx);
+}
+
+int af3_attention(void* stream, const void* q, int ldq, const void* k, const void* v, int ldk, int kv_layout, int Tk_pitch,
+                  void* out, int ldo, int B, int H, int Hkv, int D, int Tq, int Tk, float scale, int causal,
+                  const int* kv_len, const int* kv_start) {
+    return af3::attention(S(stream), B16(q), ldq, B16(k), B16(v), ldk, kv_layout, Tk_pitch, B16M(out), ldo, B, H, Hkv, D,
+                          Tq, Tk, scale, causal, kv_len, kv_start);
+}
+
+int af3_rope_kv_append(void* stream, void* qkv, void* k_cache, void* v_cache, int B, int T, int H, int Hkv, int D,
+                       int Tmax, int pos0, const int* pos0_dev, const int* kv_start, const float* inv_freq) {
+    return af3::rope_kv_append(S(stream), B16M(qkv), B16M(k_cache), B16M(v_cache), B, T, H, Hkv, D, Tmax, pos0, pos0_dev,
+                               kv_start, inv_freq);
+}
+
+size_t af3_decode_attention_scratch_bytes(int B, int H, int D) { return af3::decode_attention_scratch_bytes(B, H, D); }
+int af3_decode_attention(void* stream, const void* qkv, const void* k_cache, const void* v_cache, void* out,
+                         float* scratch, int B, int H, int Hkv, int D, int Tmax, const int* ctx_len,
+                         const int* kv_start, float scale) {
+    return af3::decode_attention(S(stream), B16(qkv), B16(k_cache), B16(v_cache), B16M(out), scratch, B, H, Hkv, D, Tmax,
+                                 ctx_len, kv_start, scale);
+}
+
+int af3_embed_scatter(void* stream, const int64_t* ids, int n_tok, const void* embed_table, int dim,
+                      int64_t audio_token_id, const void* audio_embeds, int n_win, int frames, const int* post_len,
+                      void* out, int* scratch_rows, int* counts) {
+    return af3::embed_scatter(S(stream), ids, n_tok, B16(embed_table), dim, audio_token_id, B16(audio_embeds), n_win,
+                              frames, post_len, B16M(out), scratch_rows, counts);
+}
+
+int af3_argmax(void* stream, const float* logits, int B, int V, int64_t* out_ids) {
+    return af3::argmax(S(stream), logits, B, V, out_ids);
+}
+
+}  // extern "C"

@@ -1,0 +1,359 @@
+// Fused softmax attention on tcgen05 tensor cores (sm_100a) for the two multi-query shapes of the AF3 path:
+//   * AF-Whisper encoder self-attention: bidirectional, 20 heads x 64, 1500 frames, optional key-padding mask
+//     ([O] AF3M:116-189 -> SDPA:40-104, mask from MASK:1001-1087 / AF3M:337-351)
+//   * Qwen2 decoder prefill: causal GQA 28:4 x 128 with left padding ([O] Q2M:206-245 -> SDPA:40-104, MASK:882)
+// replacing F.scaled_dot_product_attention.  One CTA = 128 query rows of one (batch, head):
+//   warp 0     TMA producer: Q tile once, then K_j / V_j tiles (128 keys x D, 128B-swizzled) through a 3-slot ring
+//   warp 1     MMA issuer:  S = Q K_j^T  (UMMA 128x128x16, fp32 in TMEM), then  O += P_j V_j  (UMMA 128xDx16, V as
+//              MN-major B operand straight from the row-major tile, P as K-major A operand from shared memory)
+//   warps 2-5  softmax: one thread per query row (= TMEM lane): two passes of tcgen05.ld over S (row max, then
+//              exp2 / row sum / bf16 P written into the swizzled smem layout the UMMA descriptor expects),
+//              O stays in TMEM and is rescaled lazily (only when the running max grew by > 2^8, FA-style).
+// Scores never touch HBM; HBM traffic is Q + K + V + O once per (batch, head) (K/V re-reads hit L2).
+#include "common.h"
+#include "ptx.cuh"
+
+namespace af3 {
+
+constexpr int AT_BM = 128;   // query rows per CTA
+constexpr int AT_BN = 128;   // keys per tile
+constexpr int AT_NSTG = 3;   // K/V ring slots
+constexpr float LOG2E = 1.4426950408889634f;
+
+struct AttnArgs {
+    int Tq, Tk, H, Hkv, causal, kv_layout;
+    float scale_log2;  // softmax scale * log2(e)
+    const int* kv_len;
+    const int* kv_start;
+    bf16* out;
+    int ldo;
+};
+
+template <int D>
+struct AttnCfg {
+    static constexpr int TILE_BYTES = AT_BN * D * 2;       // one K or V tile
+    static constexpr int Q_BYTES = AT_BM * D * 2;
+    static constexpr int P_BYTES = AT_BM * AT_BN * 2;
+    static constexpr int SMEM_BYTES = Q_BYTES + P_BYTES + AT_NSTG * TILE_BYTES + 1024 + 128;
+    static constexpr int TMEM_COLS = 256;                  // S: 128 cols, O: D cols
+};
+
+__device__ __forceinline__ void attn_tile_range(const AttnArgs& a, int b, int q0, int& j_lo, int& j_hi) {
+    const int kvl = a.kv_len ? min(a.kv_len[b], a.Tk) : a.Tk;
+    const int kvs = a.kv_start ? a.kv_start[b] : 0;
+    int hi_key = kvl;  // exclusive
+    if (a.causal) hi_key = min(hi_key, q0 + AT_BM - 1 + (a.Tk - a.Tq) + 1);
+    j_lo = kvs / AT_BN;
+    j_hi = (hi_key + AT_BN - 1) / AT_BN;
+    if (j_hi < j_lo) j_hi = j_lo;
+}
+
+template <int D>
+__global__ void __launch_bounds__(192)
+attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                 const __grid_constant__ CUtensorMap map_v, const AttnArgs a) {
+    using Cfg = AttnCfg<D>;
+    constexpr int DB = D / 64;  // 64-wide column blocks per tile
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sQ = smem;
+    uint8_t* sP = sQ + Cfg::Q_BYTES;
+    uint8_t* sKV = sP + Cfg::P_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + AT_NSTG * Cfg::TILE_BYTES);
+    uint64_t* q_full = bars;
+    uint64_t* kv_full = bars + 1;
+    uint64_t* kv_empty = kv_full + AT_NSTG;
+    uint64_t* s_full = kv_empty + AT_NSTG;
+    uint64_t* p_full = s_full + 1;
+    uint64_t* o_full = p_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * AT_BM, h = blockIdx.y, b = blockIdx.z;
+    const int hk = h / (a.H / a.Hkv);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_q);
+        tma_prefetch_desc(&map_k);
+        tma_prefetch_desc(&map_v);
+        mbar_init(q_full, 1);
+        for (int i = 0; i < AT_NSTG; ++i) {
+            mbar_init(&kv_full[i], 1);
+            mbar_init(&kv_empty[i], 1);
+        }
+        mbar_init(s_full, 1);
+        mbar_init(p_full, 128);
+        mbar_init(o_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + AT_BN;
+
+    int j_lo, j_hi;
+    attn_tile_range(a, b, q0, j_lo, j_hi);
+    const int n_tiles = j_hi - j_lo;
+
+    if (warp == 0) {
+        if (lane == 0 && n_tiles > 0) {
+            mbar_arrive_expect_tx(q_full, Cfg::Q_BYTES);
+#pragma unroll
+            for (int db = 0; db < DB; ++db) tma_load_3d(sQ + db * 16384, &map_q, q_full, h * D + db * 64, q0, b);
+            int slot = 0;
+            uint32_t phase = 0;
+            for (int j = j_lo; j < j_hi; ++j) {
+#pragma unroll
+                for (int kv = 0; kv < 2; ++kv) {
+                    mbar_wait(&kv_empty[slot], phase ^ 1);
+                    mbar_arrive_expect_tx(&kv_full[slot], Cfg::TILE_BYTES);
+                    uint8_t* dst = sKV + slot * Cfg::TILE_BYTES;
+                    const CUtensorMap* mp = kv ? &map_v : &map_k;
+#pragma unroll
+                    for (int db = 0; db < DB; ++db) {
+                        if (a.kv_layout)
+                            tma_load_3d(dst + db * 16384, mp, &kv_full[slot], db * 64, j * AT_BN, b * a.Hkv + hk);
+                        else
+                            tma_load_3d(dst + db * 16384, mp, &kv_full[slot], hk * D + db * 64, j * AT_BN, b);
+                    }
+                    if (++slot == AT_NSTG) {
+                        slot = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0 && n_tiles > 0) {
+            constexpr uint32_t idesc_s = make_idesc_bf16(AT_BM, AT_BN, 0, 0);
+            constexpr uint32_t idesc_o = make_idesc_bf16(AT_BM, D, 0, 1);  // B (= V) is MN-major
+            const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
+            mbar_wait(q_full, 0);
+            int slot = 0;
+            uint32_t phase = 0;
+            for (int t = 0; t < n_tiles; ++t) {
+                // ---- S = Q K^T
+                mbar_wait(&kv_full[slot], phase);
+                tc_fence_after();
+                {
+                    const uint32_t aK = smem_u32(sKV + slot * Cfg::TILE_BYTES);
+#pragma unroll
+                    for (int kk = 0; kk < D / 16; ++kk) {
+                        const uint32_t off = (kk >> 2) * 16384 + (kk & 3) * 32;
+                        umma_bf16_ss(tmem_S, make_smem_desc_sw128(aQ + off, 0, 1024), make_smem_desc_sw128(aK + off, 0, 1024),
+                                     idesc_s, kk != 0);
+                    }
+                    umma_commit(&kv_empty[slot]);
+                    umma_commit(s_full);
+                }
+                if (++slot == AT_NSTG) {
+                    slot = 0;
+                    phase ^= 1;
+                }
+                // ---- O += P V
+                mbar_wait(p_full, t & 1);
+                mbar_wait(&kv_full[slot], phase);
+                tc_fence_after();
+                {
+                    const uint32_t aV = smem_u32(sKV + slot * Cfg::TILE_BYTES);
+#pragma unroll
+                    for (int kk = 0; kk < AT_BN / 16; ++kk) {
+                        const uint64_t adesc = make_smem_desc_sw128(aP + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024);
+                        const uint64_t bdesc = make_smem_desc_sw128(aV + kk * 2048, 16384, 1024);
+                        umma_bf16_ss(tmem_O, adesc, bdesc, idesc_o, (t | kk) != 0);
+                    }
+                    umma_commit(&kv_empty[slot]);
+                    umma_commit(o_full);
+                }
+                if (++slot == AT_NSTG) {
+                    slot = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        const int qd = warp & 3;
+        const int row = qd * 32 + lane;        // query row within the tile = TMEM lane
+        const int qi = q0 + row;               // query index
+        const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
+        const int kvl = a.kv_len ? min(a.kv_len[b], a.Tk) : a.Tk;
+        const int kvs = a.kv_start ? a.kv_start[b] : 0;
+        const int causal_hi = a.causal ? qi + (a.Tk - a.Tq) : 0x7fffffff;  // last visible key (inclusive)
+        float m_ref = -INFINITY, l_run = 0.f;
+        const float sl2 = a.scale_log2;
+
+        for (int t = 0; t < n_tiles; ++t) {
+            const int k0 = (j_lo + t) * AT_BN;
+            mbar_wait(s_full, t & 1);
+            tc_fence_after();
+            const bool need_mask = (k0 < kvs) || (k0 + AT_BN > kvl) || (a.causal && k0 + AT_BN - 1 > q0 + (a.Tk - a.Tq));
+            // ---- pass 1: row max
+            float m_tile = -INFINITY;
+#pragma unroll 1
+            for (int c = 0; c < AT_BN / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld32(tmem_S + lane_off + c * 32, v);
+                tmem_ld_wait();
+                if (need_mask) {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        const int key = k0 + c * 32 + e;
+                        const bool ok = key >= kvs && key < kvl && key <= causal_hi;
+                        m_tile = fmaxf(m_tile, ok ? __uint_as_float(v[e]) : -INFINITY);
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) m_tile = fmaxf(m_tile, __uint_as_float(v[e]));
+                }
+            }
+            m_tile *= sl2;  // sl2 > 0: max commutes with the scale
+            const float m_new = fmaxf(m_ref, m_tile);
+            // ---- wait until P.V of the previous tile retired: P buffer and O are ours again
+            float alpha = 1.f;
+            if (t > 0) {
+                mbar_wait(o_full, (t - 1) & 1);
+                tc_fence_after();
+                const bool grow = (m_new - m_ref) > 8.0f;  // also true when m_ref == -inf and m_new finite
+                if (__any_sync(0xffffffffu, grow)) {
+                    if (grow) {
+                        alpha = (m_ref == -INFINITY) ? 0.f : exp2f(m_ref - m_new);
+                        m_ref = m_new;
+                    }
+#pragma unroll 1
+                    for (int c = 0; c < D / 32; ++c) {
+                        uint32_t o[32];
+                        tmem_ld32(tmem_O + lane_off + c * 32, o);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+                        tmem_st32(tmem_O + lane_off + c * 32, o);
+                    }
+                    tmem_st_wait();
+                }
+            } else {
+                m_ref = m_new;
+            }
+            const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
+            // ---- pass 2: probabilities -> bf16 P in the K-major 128B-swizzled layout, row sums in fp32
+            float l_tile = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < AT_BN / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld32(tmem_S + lane_off + c * 32, v);
+                tmem_ld_wait();
+                float p[32];
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    const int key = k0 + c * 32 + e;
+                    const bool ok = !need_mask || (key >= kvs && key < kvl && key <= causal_hi);
+                    p[e] = ok ? exp2f(__uint_as_float(v[e]) * sl2 - m_use) : 0.f;
+                    l_tile += p[e];
+                }
+                // keys c*32 .. c*32+31 of this row: block kb = c/2, 16-byte chunks (c&1)*4 .. +3
+                uint8_t* prow = sP + (c >> 1) * 16384 + row * 128;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int chunk = (c & 1) * 4 + g;
+                    const uint4 pk = make_uint4(pack_bf16x2(p[8 * g], p[8 * g + 1]), pack_bf16x2(p[8 * g + 2], p[8 * g + 3]),
+                                                pack_bf16x2(p[8 * g + 4], p[8 * g + 5]), pack_bf16x2(p[8 * g + 6], p[8 * g + 7]));
+                    *reinterpret_cast<uint4*>(prow + ((chunk ^ (row & 7)) << 4)) = pk;
+                }
+            }
+            l_run = l_run * alpha + l_tile;
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(p_full);
+        }
+
+        // ---- epilogue: O / l -> bf16 -> global
+        if (n_tiles > 0) {
+            mbar_wait(o_full, (n_tiles - 1) & 1);
+            tc_fence_after();
+        }
+        const float inv_l = (l_run > 0.f) ? 1.0f / l_run : 0.f;
+        bf16* orow = a.out + (static_cast<size_t>(b) * a.Tq + qi) * a.ldo + h * D;
+#pragma unroll 1
+        for (int c = 0; c < D / 32; ++c) {
+            uint32_t o[32];
+            if (n_tiles > 0) {
+                tmem_ld32(tmem_O + lane_off + c * 32, o);
+                tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int e = 0; e < 32; ++e) o[e] = 0u;
+            }
+            if (qi < a.Tq) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const uint4 pk = make_uint4(
+                        pack_bf16x2(__uint_as_float(o[8 * g]) * inv_l, __uint_as_float(o[8 * g + 1]) * inv_l),
+                        pack_bf16x2(__uint_as_float(o[8 * g + 2]) * inv_l, __uint_as_float(o[8 * g + 3]) * inv_l),
+                        pack_bf16x2(__uint_as_float(o[8 * g + 4]) * inv_l, __uint_as_float(o[8 * g + 5]) * inv_l),
+                        pack_bf16x2(__uint_as_float(o[8 * g + 6]) * inv_l, __uint_as_float(o[8 * g + 7]) * inv_l));
+                    reinterpret_cast<uint4*>(orow + c * 32)[g] = pk;
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <int D>
+static int launch_attention(cudaStream_t stream, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
+                            const AttnArgs& a, int B) {
+    using Cfg = AttnCfg<D>;
+    auto kern = attention_kernel<D>;
+    static bool configured = false;
+    if (!configured) {
+        AF3_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        configured = true;
+    }
+    dim3 grid(ceil_div(a.Tq, AT_BM), a.H, B);
+    kern<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(mq, mk, mv, a);
+    AF3_CHECK_LAUNCH();
+    return 0;
+}
+
+int attention(cudaStream_t stream, const bf16* q, int ldq, const bf16* k, const bf16* v, int ldk, int kv_layout,
+              int Tk_pitch, bf16* out, int ldo, int B, int H, int Hkv, int D, int Tq, int Tk, float scale, int causal,
+              const int* kv_len, const int* kv_start) {
+    AF3_REQUIRE(D == 64 || D == 128, "attention: head_dim must be 64 or 128");
+    AF3_REQUIRE(H % Hkv == 0, "attention: H must be a multiple of Hkv");
+    AF3_REQUIRE(ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "attention: output must be 16-byte aligned");
+    if (B <= 0 || Tq <= 0) return 0;
+    AttnArgs a{};
+    a.Tq = Tq;
+    a.Tk = Tk;
+    a.H = H;
+    a.Hkv = Hkv;
+    a.causal = causal;
+    a.kv_layout = kv_layout;
+    a.scale_log2 = scale * LOG2E;
+    a.kv_len = kv_len;
+    a.kv_start = kv_start;
+    a.out = out;
+    a.ldo = ldo;
+    CUtensorMap mq, mk, mv;
+    if (int e = make_tmap_3d(&mq, q, (uint64_t)H * D, Tq, B, ldq, (uint64_t)Tq * ldq, 64, AT_BM, 1)) return e;
+    if (kv_layout) {
+        if (int e = make_tmap_3d(&mk, k, D, Tk, (uint64_t)B * Hkv, ldk, (uint64_t)Tk_pitch * ldk, 64, AT_BN, 1)) return e;
+        if (int e = make_tmap_3d(&mv, v, D, Tk, (uint64_t)B * Hkv, ldk, (uint64_t)Tk_pitch * ldk, 64, AT_BN, 1)) return e;
+    } else {
+        if (int e = make_tmap_3d(&mk, k, (uint64_t)Hkv * D, Tk, B, ldk, (uint64_t)Tk * ldk, 64, AT_BN, 1)) return e;
+        if (int e = make_tmap_3d(&mv, v, (uint64_t)Hkv * D, Tk, B, ldk, (uint64_t)Tk * ldk, 64, AT_BN, 1)) return e;
+    }
+    if (D == 64) return launch_attention<64>(stream, mq, mk, mv, a, B);
+    return launch_attention<128>(stream, mq, mk, mv, a, B);
+}
+
+}  // namespace af3

@@ -1,0 +1,45 @@
+// Host-side helpers shared by all translation units of libaf3b200.so:
+// error reporting for the C ABI, TMA tensor-map construction (driver entry point fetched at run time so the
+// library links against cudart only), and device properties.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+namespace af3 {
+
+typedef __nv_bfloat16 bf16;
+
+void set_last_error(const std::string& msg);
+int fail(const std::string& msg);  // records msg, returns a non-zero status
+
+#define AF3_CHECK_CUDA(expr)                                                                        \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            return af3::fail(std::string(#expr) + " -> " + cudaGetErrorString(_e) + " @" + __FILE__ + \
+                             ":" + std::to_string(__LINE__));                                       \
+    } while (0)
+
+#define AF3_CHECK_LAUNCH() AF3_CHECK_CUDA(cudaGetLastError())
+
+#define AF3_REQUIRE(cond, msg)                                          \
+    do {                                                                \
+        if (!(cond)) return af3::fail(std::string("af3: ") + (msg));    \
+    } while (0)
+
+// bf16 row-major tensor maps with 128-byte swizzle; box inner extent is always 64 elements (128 B).
+// 2-D: dims (inner = cols, outer = rows), row pitch in elements.
+int make_tmap_2d(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint64_t pitch_elems,
+                 uint32_t box_cols, uint32_t box_rows);
+// 3-D: dims (d0 = cols, d1, d2) with element pitches p1, p2.
+int make_tmap_3d(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t p1_elems,
+                 uint64_t p2_elems, uint32_t box0, uint32_t box1, uint32_t box2);
+
+int sm_count();
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace af3

@@ -1,0 +1,480 @@
+// HBM-bound CUDA-core kernels of the AF3 path: LayerNorm, AvgPool+LayerNorm, RMSNorm, conv-stem im2col,
+// rotary embedding + KV-cache append, embedding gather / audio-row scatter, gate/up weight packing, argmax.
+// All bf16 tensors are accessed with 16-byte vector loads/stores, one warp (or a few) per row, fp32 statistics,
+// and the reference's bf16 rounding points are reproduced op by op (cited per kernel).
+#include "common.h"
+#include "ptx.cuh"
+
+namespace af3 {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float2 t = __bfloat1622float2(h[e]);
+        f[2 * e] = t.x;
+        f[2 * e + 1] = t.y;
+    }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+
+constexpr int NORM_MAXV = 16;  // uint4 chunks per lane -> dim <= 4096
+
+// ---------------------------------------------------------------------------------------------------------
+// LayerNorm ([O] AF3M:224,232,366: nn.LayerNorm, eps 1e-5; fp32 statistics, one rounding to bf16).
+// POOL: the row is first formed as bf16((x[2t] + x[2t+1]) / 2)  (nn.AvgPool1d(2,2), AF3M:364-365).
+template <bool POOL>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const bf16* __restrict__ gamma,
+                 const bf16* __restrict__ beta, int rows, int dim, float eps, int T_in, int T_out) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const int nchunk = dim >> 3;
+    float v[NORM_MAXV][8];
+    float sum = 0.f;
+    size_t in_row = row;
+    if (POOL) {
+        const int w = row / T_out, t = row - w * T_out;
+        in_row = static_cast<size_t>(w) * T_in + 2 * t;
+    }
+    const uint4* xp = reinterpret_cast<const uint4*>(x + in_row * dim);
+#pragma unroll
+    for (int i = 0; i < NORM_MAXV; ++i) {
+        const int c = lane + 32 * i;
+        if (c < nchunk) {
+            unpack8(xp[c], v[i]);
+            if (POOL) {
+                float b[8];
+                unpack8(xp[c + nchunk], b);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[i][e] = bf16_round((v[i][e] + b[e]) * 0.5f);
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) sum += v[i][e];
+        }
+    }
+    const float mean = warp_sum(sum) / dim;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NORM_MAXV; ++i) {
+        const int c = lane + 32 * i;
+        if (c < nchunk) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float d = v[i][e] - mean;
+                sq += d * d;
+            }
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / dim + eps);
+    uint4* yp = reinterpret_cast<uint4*>(y + static_cast<size_t>(row) * dim);
+    const uint4* gp = reinterpret_cast<const uint4*>(gamma);
+    const uint4* bp = reinterpret_cast<const uint4*>(beta);
+#pragma unroll
+    for (int i = 0; i < NORM_MAXV; ++i) {
+        const int c = lane + 32 * i;
+        if (c < nchunk) {
+            float g[8], b[8], o[8];
+            unpack8(__ldg(gp + c), g);
+            unpack8(__ldg(bp + c), b);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = (v[i][e] - mean) * rstd * g[e] + b[e];
+            yp[c] = pack8(o);
+        }
+    }
+}
+
+int layernorm(cudaStream_t stream, const bf16* x, bf16* y, const bf16* gamma, const bf16* beta, int rows, int dim,
+              float eps) {
+    AF3_REQUIRE(dim % 8 == 0 && dim <= NORM_MAXV * 256, "layernorm: dim must be a multiple of 8 and <= 4096");
+    if (rows <= 0) return 0;
+    layernorm_kernel<false><<<ceil_div(rows, 8), 256, 0, stream>>>(x, y, gamma, beta, rows, dim, eps, 0, 0);
+    AF3_CHECK_LAUNCH();
+    return 0;
+}
+int avgpool_layernorm(cudaStream_t stream, const bf16* x, bf16* y, const bf16* gamma, const bf16* beta, int n_win,
+                      int T, int dim, float eps) {
+    AF3_REQUIRE(dim % 8 == 0 && dim <= NORM_MAXV * 256, "avgpool_layernorm: dim must be a multiple of 8 and <= 4096");
+    const int T_out = T / 2;
+    const int rows = n_win * T_out;
+    if (rows <= 0) return 0;
+    layernorm_kernel<true><<<ceil_div(rows, 8), 256, 0, stream>>>(x, y, gamma, beta, rows, dim, eps, T, T_out);
+    AF3_CHECK_LAUNCH();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Qwen2RMSNorm ([O] Q2M:258-263): h = x.float(); h = h * rsqrt(mean(h^2) + eps); return weight * h.to(bf16).
+__global__ void __launch_bounds__(256)
+rmsnorm_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const bf16* __restrict__ weight, int rows, int dim,
+               float eps, const int* __restrict__ row_idx) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const size_t in_row = row_idx ? static_cast<size_t>(row_idx[row]) : static_cast<size_t>(row);
+    const int nchunk = dim >> 3;
+    const uint4* xp = reinterpret_cast<const uint4*>(x + in_row * dim);
+    float v[NORM_MAXV][8];
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NORM_MAXV; ++i) {
+        const int c = lane + 32 * i;
+        if (c < nchunk) {
+            unpack8(xp[c], v[i]);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) sq += v[i][e] * v[i][e];
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / dim + eps);
+    uint4* yp = reinterpret_cast<uint4*>(y + static_cast<size_t>(row) * dim);
+    const uint4* wp = reinterpret_cast<const uint4*>(weight);
+#pragma unroll
+    for (int i = 0; i < NORM_MAXV; ++i) {
+        const int c = lane + 32 * i;
+        if (c < nchunk) {
+            float w[8], o[8];
+            unpack8(__ldg(wp + c), w);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = w[e] * bf16_round(v[i][e] * rstd);
+            yp[c] = pack8(o);
+        }
+    }
+}
+
+int rmsnorm(cudaStream_t stream, const bf16* x, bf16* y, const bf16* weight, int rows, int dim, float eps,
+            const int* row_idx) {
+    AF3_REQUIRE(dim % 8 == 0 && dim <= NORM_MAXV * 256, "rmsnorm: dim must be a multiple of 8 and <= 4096");
+    if (rows <= 0) return 0;
+    rmsnorm_kernel<<<ceil_div(rows, 8), 256, 0, stream>>>(x, y, weight, rows, dim, eps, row_idx);
+    AF3_CHECK_LAUNCH();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// conv1 im2col ([O] AF3M:343: conv1d(k=3, pad=1) over [n_win, C, T]): cols[(w,t)][kk*C + c] = bf16(x[w][c][t+kk-1]).
+// A CTA transposes a [C x 64(+2)] slab through shared memory: reads coalesced along t, writes 16 B along c.
+template <typename TIn>
+__global__ void __launch_bounds__(256)
+im2col_conv1_kernel(const TIn* __restrict__ in, bf16* __restrict__ cols, int C, int T) {
+    extern __shared__ bf16 tile[];  // [C][66 + 2 pad]
+    constexpr int TB = 64, P = 68;
+    const int w = blockIdx.y, t0 = blockIdx.x * TB;
+    const TIn* xin = in + static_cast<size_t>(w) * C * T;
+    for (int i = threadIdx.x; i < C * (TB + 2); i += blockDim.x) {
+        const int c = i / (TB + 2), tt = i - c * (TB + 2);
+        const int t = t0 + tt - 1;
+        float v = 0.f;
+        if (t >= 0 && t < T) v = static_cast<float>(xin[static_cast<size_t>(c) * T + t]);
+        tile[c * P + tt] = __float2bfloat16_rn(v);
+    }
+    __syncthreads();
+    const int cpr = 3 * C / 8;  // uint4 chunks per output row
+    for (int i = threadIdx.x; i < TB * cpr; i += blockDim.x) {
+        const int tl = i / cpr, ch = i - tl * cpr;
+        const int t = t0 + tl;
+        if (t >= T) continue;
+        const int kk = (ch * 8) / C, c0 = ch * 8 - kk * C;
+        uint32_t pk[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const bf16 a = tile[(c0 + 2 * e) * P + tl + kk];
+            const bf16 b = tile[(c0 + 2 * e + 1) * P + tl + kk];
+            pk[e] = static_cast<uint32_t>(__bfloat16_as_ushort(a)) | (static_cast<uint32_t>(__bfloat16_as_ushort(b)) << 16);
+        }
+        reinterpret_cast<uint4*>(cols + (static_cast<size_t>(w) * T + t) * 3 * C)[ch] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+}
+
+int im2col_conv1(cudaStream_t stream, const void* in, int in_is_f32, bf16* cols, int n_win, int C, int T) {
+    AF3_REQUIRE(C % 8 == 0, "im2col_conv1: C must be a multiple of 8");
+    if (n_win <= 0) return 0;
+    dim3 grid(ceil_div(T, 64), n_win);
+    const size_t smem = static_cast<size_t>(C) * 68 * sizeof(bf16);
+    if (in_is_f32)
+        im2col_conv1_kernel<float><<<grid, 256, smem, stream>>>(static_cast<const float*>(in), cols, C, T);
+    else
+        im2col_conv1_kernel<bf16><<<grid, 256, smem, stream>>>(static_cast<const bf16*>(in), cols, C, T);
+    AF3_CHECK_LAUNCH();
+    return 0;
+}
+
+// conv2 im2col ([O] AF3M:344: conv1d(k=3, stride=2, pad=1)) on the channel-last activation [n_win*T, C]:
+// output row (w, t') is the concatenation of input rows 2t'-1, 2t', 2t'+1 (zero outside [0, T)).
+__global__ void __launch_bounds__(256)
+im2col_conv2_kernel(const bf16* __restrict__ in, bf16* __restrict__ cols, int C, int T, int T_out, long long total16) {
+    const int cpr = 3 * C / 8;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total16;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long row = i / cpr;
+        const int ch = static_cast<int>(i - row * cpr);
+        const int w = static_cast<int>(row / T_out), tp = static_cast<int>(row - static_cast<long long>(w) * T_out);
+        const int kk = (ch * 8) / C, c0 = ch * 8 - kk * C;
+        const int t = 2 * tp + kk - 1;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (t >= 0 && t < T) v = *reinterpret_cast<const uint4*>(in + (static_cast<size_t>(w) * T + t) * C + c0);
+        reinterpret_cast<uint4*>(cols)[i] = v;
+    }
+}
+
+int im2col_conv2(cudaStream_t stream, const bf16* in, bf16* cols, int n_win, int C, int T) {
+    AF3_REQUIRE(C % 8 == 0, "im2col_conv2: C must be a multiple of 8");
+    const int T_out = (T - 1) / 2 + 1;
+    const long long total16 = static_cast<long long>(n_win) * T_out * (3 * C / 8);
+    if (total16 <= 0) return 0;
+    const int grid = static_cast<int>(((total16 + 255) / 256) < 148ll * 16 ? ((total16 + 255) / 256) : 148ll * 16);
+    im2col_conv2_kernel<<<grid, 256, 0, stream>>>(in, cols, C, T, T_out, total16);
+    AF3_CHECK_LAUNCH();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// gate/up interleave for the fused SwiGLU GEMM: per 128 features, 128 gate rows then 128 up rows (zero padded).
+__global__ void pack_gate_up_kernel(const bf16* __restrict__ gate, const bf16* __restrict__ up, bf16* __restrict__ packed,
+                                    int F, int K, long long total16) {
+    const int cpr = K / 8;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total16;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long prow = i / cpr;
+        const int ch = static_cast<int>(i - prow * cpr);
+        const int blk = static_cast<int>(prow / 256), within = static_cast<int>(prow % 256);
+        const int f = blk * 128 + (within & 127);
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (f < F) v = reinterpret_cast<const uint4*>((within < 128 ? gate : up) + static_cast<size_t>(f) * K)[ch];
+        reinterpret_cast<uint4*>(packed)[i] = v;
+    }
+}
+int pack_gate_up(cudaStream_t stream, const bf16* gate, const bf16* up, bf16* packed, int F, int K) {
+    AF3_REQUIRE(K % 8 == 0, "pack_gate_up: K must be a multiple of 8");
+    const long long total16 = 2ll * ceil_div(F, 128) * 128 * (K / 8);
+    const int grid = static_cast<int>(((total16 + 255) / 256) < 148ll * 16 ? ((total16 + 255) / 256) : 148ll * 16);
+    pack_gate_up_kernel<<<grid, 256, 0, stream>>>(gate, up, packed, F, K, total16);
+    AF3_CHECK_LAUNCH();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Rotary embedding + KV append ([O] Q2M:100-146 rotate-half RoPE with fp32 tables cast to bf16; CACHE:119-120).
+// One thread = one (token, head, i < D/2) pair (i, i + D/2).  Every bf16 op of the reference rounds: q*cos,
+// rotate_half(q)*sin and their sum are each rounded to bf16.
+__global__ void __launch_bounds__(256)
+rope_kv_append_kernel(bf16* __restrict__ qkv, bf16* __restrict__ k_cache, bf16* __restrict__ v_cache, int B, int T,
+                      int H, int Hkv, int D, int Tmax, int pos0, const int* __restrict__ pos0_dev,
+                      const int* __restrict__ kv_start, const float* __restrict__ inv_freq) {
+    const int half = D >> 1;
+    const int heads = H + 2 * Hkv;
+    const long long total = static_cast<long long>(B) * T * heads * half;
+    const int p0 = pos0_dev ? *pos0_dev : pos0;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int d = static_cast<int>(i % half);
+        long long r = i / half;
+        const int h = static_cast<int>(r % heads);
+        r /= heads;
+        const int t = static_cast<int>(r % T);
+        const int b = static_cast<int>(r / T);
+        bf16* row = qkv + (static_cast<size_t>(b) * T + t) * heads * D + static_cast<size_t>(h) * D;
+        const int cpos = p0 + t;  // cache slot
+        if (h >= H + Hkv) {       // value head: plain copy into the cache
+            const int hk = h - H - Hkv;
+            bf16* dst = v_cache + ((static_cast<size_t>(b) * Hkv + hk) * Tmax + cpos) * D;
+            dst[d] = row[d];
+            dst[d + half] = row[d + half];
+            continue;
+        }
+        int pos = cpos - (kv_start ? kv_start[b] : 0);
+        if (pos < 0) pos = 1;  // padded slot: position_ids.masked_fill_(mask == 0, 1) (GEN:721)
+        const float fr = inv_freq[d] * static_cast<float>(pos);
+        const float c = bf16_round(cosf(fr)), s = bf16_round(sinf(fr));
+        const float x1 = __bfloat162float(row[d]), x2 = __bfloat162float(row[d + half]);
+        const float o1 = bf16_round(bf16_round(x1 * c) + bf16_round(-x2 * s));
+        const float o2 = bf16_round(bf16_round(x2 * c) + bf16_round(x1 * s));
+        if (h < H) {
+            row[d] = __float2bfloat16_rn(o1);
+            row[d + half] = __float2bfloat16_rn(o2);
+        } else {
+            const int hk = h - H;
+            bf16* dst = k_cache + ((static_cast<size_t>(b) * Hkv + hk) * Tmax + cpos) * D;
+            dst[d] = __float2bfloat16_rn(o1);
+            dst[d + half] = __float2bfloat16_rn(o2);
+        }
+    }
+}
+
+int rope_kv_append(cudaStream_t stream, bf16* qkv, bf16* k_cache, bf16* v_cache, int B, int T, int H, int Hkv, int D,
+                   int Tmax, int pos0, const int* pos0_dev, const int* kv_start, const float* inv_freq) {
+    AF3_REQUIRE(D % 2 == 0 && inv_freq, "rope: bad head dim / missing inv_freq");
+    AF3_REQUIRE(pos0_dev || pos0 + T <= Tmax, "rope: KV cache overflow");
+    const long long total = static_cast<long long>(B) * T * (H + 2 * Hkv) * (D / 2);
+    if (total <= 0) return 0;
+    const int grid = static_cast<int>(((total + 255) / 256) < 148ll * 32 ? ((total + 255) / 256) : 148ll * 32);
+    rope_kv_append_kernel<<<grid, 256, 0, stream>>>(qkv, k_cache, v_cache, B, T, H, Hkv, D, Tmax, pos0, pos0_dev, kv_start,
+                                                   inv_freq);
+    AF3_CHECK_LAUNCH();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Embedding gather + audio scatter ([O] AF3M:557 embed_tokens; :469-473 valid-frame select; :563-566 masked_scatter).
+// Kernel 1 (one CTA): exclusive scan of (ids == audio_token_id) over the flattened prompt -> ordinal of each audio
+// token; exclusive scan of post_len -> first ordinal of each window.  Kernel 2: one warp per token row copy.
+__global__ void __launch_bounds__(1024)
+scatter_index_kernel(const int64_t* __restrict__ ids, int n_tok, int64_t audio_id, const int* __restrict__ post_len,
+                     int n_win, int frames, int* __restrict__ src_row /*[n_tok]*/, int* __restrict__ counts) {
+    __shared__ int warp_tot[32];
+    __shared__ int carry;
+    __shared__ int win_base[1025];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // window prefix (n_win <= 1024 handled in one sweep; larger handled serially by thread 0)
+    if (tid == 0) {
+        int acc = 0;
+        for (int w = 0; w < n_win; ++w) {
+            if (w < 1025) win_base[w] = acc;
+            acc += min(post_len[w], frames);
+        }
+        counts[1] = acc;
+        carry = 0;
+    }
+    __syncthreads();
+    for (int base = 0; base < n_tok; base += 1024) {
+        const int i = base + tid;
+        const int flag = (i < n_tok && ids[i] == audio_id) ? 1 : 0;
+        int incl = flag;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int v = warp_tot[lane], inc2 = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int n = __shfl_up_sync(0xffffffffu, inc2, o);
+                if (lane >= o) inc2 += n;
+            }
+            warp_tot[lane] = inc2 - v;  // exclusive
+            if (lane == 31) win_base[1024] = inc2;  // block total (scratch slot)
+        }
+        __syncthreads();
+        const int ord = carry + warp_tot[warp] + incl - flag;
+        if (i < n_tok) {
+            int row = -1;
+            if (flag) {
+                // binary search the window whose [base, base+len) contains ord
+                int lo = 0, hi = n_win - 1;
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (win_base[mid] <= ord) lo = mid; else hi = mid - 1;
+                }
+                const int off = ord - win_base[lo];
+                row = (off < min(post_len[lo], frames)) ? lo * frames + off : -2;  // -2: more tokens than features
+            }
+            src_row[i] = row;
+        }
+        __syncthreads();
+        if (tid == 0) carry += win_base[1024];
+        __syncthreads();
+    }
+    if (tid == 0) counts[0] = carry;
+}
+
+__global__ void __launch_bounds__(256)
+embed_scatter_kernel(const int64_t* __restrict__ ids, int n_tok, const bf16* __restrict__ table, int dim,
+                     const bf16* __restrict__ audio, const int* __restrict__ src_row, bf16* __restrict__ out) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= n_tok) return;
+    const int sr = src_row[row];
+    const bf16* src = (sr >= 0) ? audio + static_cast<size_t>(sr) * dim : table + static_cast<size_t>(ids[row]) * dim;
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(out + static_cast<size_t>(row) * dim);
+    for (int c = lane; c < dim / 8; c += 32) d4[c] = __ldg(s4 + c);
+}
+
+int embed_scatter(cudaStream_t stream, const int64_t* ids, int n_tok, const bf16* table, int dim, int64_t audio_id,
+                  const bf16* audio, int n_win, int frames, const int* post_len, bf16* out, int* src_row_scratch,
+                  int* counts) {
+    AF3_REQUIRE(dim % 8 == 0, "embed_scatter: dim must be a multiple of 8");
+    AF3_REQUIRE(n_win <= 1024, "embed_scatter: at most 1024 windows per call");
+    if (n_tok <= 0) return 0;
+    static const int zero_len = 0;
+    (void)zero_len;
+    scatter_index_kernel<<<1, 1024, 0, stream>>>(ids, n_tok, audio_id, post_len, n_win, frames, src_row_scratch, counts);
+    AF3_CHECK_LAUNCH();
+    embed_scatter_kernel<<<ceil_div(n_tok, 8), 256, 0, stream>>>(ids, n_tok, table, dim, audio, src_row_scratch, out);
+    AF3_CHECK_LAUNCH();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Greedy argmax over fp32 logits ([O] GEN:2762 logits.float(), :2793 torch.argmax -> first maximal index).
+__global__ void __launch_bounds__(1024)
+argmax_kernel(const float* __restrict__ logits, int V, int64_t* __restrict__ out) {
+    const float* p = logits + static_cast<size_t>(blockIdx.x) * V;
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    const int n4 = ((reinterpret_cast<uintptr_t>(p) & 15) == 0) ? V / 4 : 0;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+        const float4 v = reinterpret_cast<const float4*>(p)[i];
+        const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (e[j] > best || (e[j] == best && 4 * i + j < bi)) {
+                best = e[j];
+                bi = 4 * i + j;
+            }
+    }
+    for (int i = n4 * 4 + threadIdx.x; i < V; i += blockDim.x)
+        if (p[i] > best || (p[i] == best && i < bi)) {
+            best = p[i];
+            bi = i;
+        }
+    __shared__ float sb[32];
+    __shared__ int si[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) {
+            best = ob;
+            bi = oi;
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+        sb[threadIdx.x >> 5] = best;
+        si[threadIdx.x >> 5] = bi;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        best = sb[threadIdx.x];
+        bi = si[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi < bi)) {
+                best = ob;
+                bi = oi;
+            }
+        }
+        if (threadIdx.x == 0) out[blockIdx.x] = (bi == 0x7fffffff) ? 0 : bi;  // all-NaN row -> 0
+    }
+}
+
+int argmax(cudaStream_t stream, const float* logits, int B, int V, int64_t* out) {
+    if (B <= 0) return 0;
+    argmax_kernel<<<B, 1024, 0, stream>>>(logits, V, out);
+    AF3_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // namespace af3

@@ -1,0 +1,242 @@
+"""Torch-tensor front ends of the C-ABI kernels (one function per entry point of include/af3b200.h).
+
+These only validate shapes/dtypes, allocate outputs with torch and pass raw pointers + the current CUDA stream
+through ctypes.  All arithmetic happens in libaf3b200.so; nothing here falls back to torch ops.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import EPI_BIAS, EPI_F32OUT, EPI_GELU, EPI_RESID, EPI_SWIGLU, check, ptr, stream_ptr
+
+bf16 = torch.bfloat16
+
+
+def _req(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise _lib.AF3Error(f"{name} must be a CUDA tensor (the AF3 hot path has no CPU fallback)")
+    if t.dtype != dtype:
+        raise _lib.AF3Error(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise _lib.AF3Error(f"{name} must be contiguous")
+    return t
+
+
+# ----------------------------------------------------------------------------------------------- GEMM
+def linear(x, w, bias=None, *, gelu=False, resid=None, res_period=0, out=None, out_f32=False):
+    """out = epi(x @ w.T); x [n_tok, K] bf16, w [n_feat, K] bf16 (nn.Linear layout)."""
+    lib = _lib.load()
+    _req(x, bf16, "x"), _req(w, bf16, "w")
+    n_tok, K = x.shape
+    n_feat = w.shape[0]
+    flags = 0
+    if bias is not None:
+        _req(bias, bf16, "bias")
+        flags |= EPI_BIAS
+    if gelu:
+        flags |= EPI_GELU
+    if resid is not None:
+        _req(resid, bf16, "resid")
+        flags |= EPI_RESID
+    if out_f32:
+        flags |= EPI_F32OUT
+    if out is None:
+        out = torch.empty((n_tok, n_feat), device=x.device, dtype=torch.float32 if out_f32 else bf16)
+    check(
+        lib.af3_gemm_bf16(stream_ptr(), ptr(x), x.stride(0), ptr(w), w.stride(0), ptr(out), out.stride(0), n_tok, n_feat,
+                          K, flags, ptr(bias), ptr(resid), resid.stride(0) if resid is not None else 0, res_period),
+        "af3_gemm_bf16",
+    )
+    return out
+
+
+def pack_gate_up(gate, up):
+    lib = _lib.load()
+    _req(gate, bf16, "gate"), _req(up, bf16, "up")
+    F, K = gate.shape
+    packed = torch.empty((2 * ((F + 127) // 128) * 128, K), device=gate.device, dtype=bf16)
+    check(lib.af3_pack_gate_up(stream_ptr(), ptr(gate), ptr(up), ptr(packed), F, K), "af3_pack_gate_up")
+    return packed
+
+
+def swiglu_linear(x, w_packed, n_feat, out=None):
+    """out = silu(x @ gate.T) * (x @ up.T) with w_packed from pack_gate_up."""
+    lib = _lib.load()
+    _req(x, bf16, "x"), _req(w_packed, bf16, "w_packed")
+    n_tok, K = x.shape
+    if out is None:
+        out = torch.empty((n_tok, n_feat), device=x.device, dtype=bf16)
+    check(
+        lib.af3_gemm_bf16(stream_ptr(), ptr(x), x.stride(0), ptr(w_packed), w_packed.stride(0), ptr(out), out.stride(0),
+                          n_tok, n_feat, K, EPI_SWIGLU, None, None, 0, 0),
+        "af3_gemm_bf16(swiglu)",
+    )
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- log-mel
+class LogMelTables:
+    """Constant tables of the log-mel kernel, built exactly as the reference builds its constants."""
+
+    def __init__(self, mel_filters_np: np.ndarray, device):
+        # mel_filters_np: [201, 128] float64/32 from transformers.audio_utils.mel_filter_bank (WFE:95-103)
+        f = np.asarray(mel_filters_np, dtype=np.float32)
+        assert f.shape == (201, 128)
+        nz = f != 0
+        klo = np.where(nz.any(0), nz.argmax(0), 0).astype(np.int32)
+        khi = np.where(nz.any(0), 200 - nz[::-1].argmax(0), -1).astype(np.int32)
+        n = np.arange(201, dtype=np.float64)[:, None]
+        k = np.arange(128, dtype=np.float64)[None, :]
+        ang = 2.0 * np.pi * n * k / 400.0
+        tab = np.stack([np.cos(ang), np.sin(ang)], axis=-1)
+        tab[:, 101:, :] = 0.0
+        self.filters = torch.from_numpy(f).to(device)
+        self.klo = torch.from_numpy(klo).to(device)
+        self.khi = torch.from_numpy(khi).to(device)
+        self.table = torch.from_numpy(tab.astype(np.float32)).to(device).contiguous()
+        self.hann = torch.hann_window(400, dtype=torch.float32).to(device)  # WFE:141
+
+
+def logmel(wave, tables: LogMelTables):
+    """wave fp32 [n_win, n_samples] -> fp32 [n_win, 128, n_samples // 160]  (WFE:135-164)."""
+    lib = _lib.load()
+    _req(wave, torch.float32, "wave")
+    n_win, n_samples = wave.shape
+    out = torch.empty((n_win, 128, n_samples // 160), device=wave.device, dtype=torch.float32)
+    scratch = torch.empty((n_win,), device=wave.device, dtype=torch.int32)
+    check(
+        lib.af3_logmel(stream_ptr(), ptr(wave), n_win, n_samples, ptr(tables.hann), ptr(tables.table), ptr(tables.filters),
+                       ptr(tables.klo), ptr(tables.khi), ptr(out), ptr(scratch)),
+        "af3_logmel",
+    )
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- conv stem
+def im2col_conv1(x):
+    """x [n_win, C, T] fp32|bf16 -> [n_win*T, 3C] bf16."""
+    lib = _lib.load()
+    if x.dtype not in (torch.float32, bf16):
+        raise _lib.AF3Error("input_features must be fp32 or bf16")
+    _req(x, x.dtype, "input_features")
+    n_win, Cc, T = x.shape
+    cols = torch.empty((n_win * T, 3 * Cc), device=x.device, dtype=bf16)
+    check(lib.af3_im2col_conv1(stream_ptr(), ptr(x), int(x.dtype == torch.float32), ptr(cols), n_win, Cc, T), "af3_im2col_conv1")
+    return cols
+
+
+def im2col_conv2(h, n_win, T):
+    """h [n_win*T, C] bf16 channel-last -> [n_win*T_out, 3C] bf16 (stride 2)."""
+    lib = _lib.load()
+    _req(h, bf16, "h")
+    Cc = h.shape[1]
+    T_out = (T - 1) // 2 + 1
+    cols = torch.empty((n_win * T_out, 3 * Cc), device=h.device, dtype=bf16)
+    check(lib.af3_im2col_conv2(stream_ptr(), ptr(h), ptr(cols), n_win, Cc, T), "af3_im2col_conv2")
+    return cols
+
+
+# ----------------------------------------------------------------------------------------------- norms
+def layernorm(x, gamma, beta, eps=1e-5, out=None):
+    lib = _lib.load()
+    _req(x, bf16, "x")
+    rows, dim = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib.af3_layernorm(stream_ptr(), ptr(x), ptr(out), ptr(gamma), ptr(beta), rows, dim, eps), "af3_layernorm")
+    return out
+
+
+def avgpool_layernorm(x, n_win, T, gamma, beta, eps=1e-5):
+    lib = _lib.load()
+    _req(x, bf16, "x")
+    dim = x.shape[1]
+    out = torch.empty((n_win * (T // 2), dim), device=x.device, dtype=bf16)
+    check(lib.af3_avgpool_layernorm(stream_ptr(), ptr(x), ptr(out), ptr(gamma), ptr(beta), n_win, T, dim, eps), "af3_avgpool_layernorm")
+    return out
+
+
+def rmsnorm(x, weight, eps=1e-6, row_idx=None, out=None):
+    lib = _lib.load()
+    _req(x, bf16, "x")
+    dim = x.shape[1]
+    rows = x.shape[0] if row_idx is None else row_idx.numel()
+    if out is None:
+        out = torch.empty((rows, dim), device=x.device, dtype=bf16)
+    check(lib.af3_rmsnorm(stream_ptr(), ptr(x), ptr(out), ptr(weight), rows, dim, eps, ptr(row_idx)), "af3_rmsnorm")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- attention
+def attention(q, k, v, out, *, B, H, Hkv, D, Tq, Tk, scale, causal, kv_layout=0, Tk_pitch=0, ldq=None, ldk=None,
+              kv_len=None, kv_start=None):
+    lib = _lib.load()
+    check(
+        lib.af3_attention(stream_ptr(), ptr(q), ldq, ptr(k), ptr(v), ldk, kv_layout, Tk_pitch, ptr(out), out.stride(-2),
+                          B, H, Hkv, D, Tq, Tk, float(scale), int(causal), ptr(kv_len), ptr(kv_start)),
+        "af3_attention",
+    )
+    return out
+
+
+def rope_kv_append(qkv, k_cache, v_cache, *, B, T, H, Hkv, D, pos0, inv_freq, kv_start=None, pos0_dev=None):
+    lib = _lib.load()
+    Tmax = k_cache.shape[2]
+    check(
+        lib.af3_rope_kv_append(stream_ptr(), ptr(qkv), ptr(k_cache), ptr(v_cache), B, T, H, Hkv, D, Tmax, pos0, ptr(pos0_dev),
+                               ptr(kv_start), ptr(inv_freq)),
+        "af3_rope_kv_append",
+    )
+
+
+def decode_attention(qkv, k_cache, v_cache, out, scratch, *, B, H, Hkv, D, ctx_len, kv_start, scale):
+    lib = _lib.load()
+    Tmax = k_cache.shape[2]
+    check(
+        lib.af3_decode_attention(stream_ptr(), ptr(qkv), ptr(k_cache), ptr(v_cache), ptr(out), ptr(scratch), B, H, Hkv, D,
+                                 Tmax, ptr(ctx_len), ptr(kv_start), float(scale)),
+        "af3_decode_attention",
+    )
+    return out
+
+
+def decode_attention_scratch(B, H, D, device):
+    n = _lib.load().af3_decode_attention_scratch_bytes(B, H, D)
+    return torch.empty((n // 4,), device=device, dtype=torch.float32)
+
+
+# ----------------------------------------------------------------------------------------------- glue
+def embed_scatter(ids, table, audio_token_id, audio_embeds, n_win, frames, post_len, out=None):
+    """ids int64 [n_tok]; returns (inputs_embeds [n_tok, dim] bf16, counts int32[2] on device)."""
+    lib = _lib.load()
+    _req(ids, torch.int64, "input_ids"), _req(table, bf16, "embed_tokens.weight")
+    n_tok = ids.numel()
+    dim = table.shape[1]
+    if out is None:
+        out = torch.empty((n_tok, dim), device=table.device, dtype=bf16)
+    scratch = torch.empty((n_tok,), device=table.device, dtype=torch.int32)
+    counts = torch.zeros((2,), device=table.device, dtype=torch.int32)
+    if audio_embeds is None:
+        audio_embeds = table  # never read: n_win = 0 -> no valid rows
+        n_win, frames = 0, 1
+        post_len = counts
+    check(
+        lib.af3_embed_scatter(stream_ptr(), ptr(ids), n_tok, ptr(table), dim, int(audio_token_id), ptr(audio_embeds), n_win,
+                              frames, ptr(post_len), ptr(out), ptr(scratch), ptr(counts)),
+        "af3_embed_scatter",
+    )
+    return out, counts
+
+
+def argmax(logits, out=None):
+    lib = _lib.load()
+    _req(logits, torch.float32, "logits")
+    B, V = logits.shape
+    if out is None:
+        out = torch.empty((B,), device=logits.device, dtype=torch.int64)
+    check(lib.af3_argmax(stream_ptr(), ptr(logits), B, V, ptr(out)), "af3_argmax")
+    return out

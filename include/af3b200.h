@@ -1,0 +1,108 @@
+/* libaf3b200.so -- C ABI of the B200-native Audio Flamingo 3 audio->text hot path.
+ *
+ * Boundary: the reference path sits behind PyTorch nn.Module call conventions, not an FFI
+ * registry, so there is no pre-existing binding to copy.  Each entry point below names the reference interface
+ * it replaces ([O] = transformers 5.5.0, the executable statement of the AF3 path):
+ *   AF3M = models/audioflamingo3/modeling_audioflamingo3.py   WFE = models/whisper/feature_extraction_whisper.py
+ *   Q2M  = models/qwen2/modeling_qwen2.py                      GEN = generation/utils.py
+ *   CACHE = cache_utils.py   SDPA = integrations/sdpa_attention.py
+ *
+ * Conventions: plain pointers and sizes only (no torch types); every pointer is a DEVICE pointer unless the
+ * parameter name starts with h_; `stream` is a cudaStream_t passed as void*; all calls are asynchronous on
+ * `stream`; return 0 on success, non-zero on error with a message available from af3_last_error() (thread
+ * local).  No ownership transfer: outputs are written into caller-allocated buffers.  Not re-entrant per
+ * engine handle; one handle per GPU.  bf16 tensors are row-major with the stated pitch.
+ */
+#ifndef AF3B200_H
+#define AF3B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* af3_last_error(void);
+int af3_abi_version(void);
+
+/* ---- epilogue flags for af3_gemm_bf16 ---- */
+#define AF3_EPI_BIAS 1
+#define AF3_EPI_GELU 2
+#define AF3_EPI_RESID 4
+#define AF3_EPI_SWIGLU 8
+#define AF3_EPI_F32OUT 16
+
+/* out[tok, feat] = epi( x[tok,:] . w[feat,:] ), tcgen05 tensor cores.  Replaces F.linear at
+ * [O] AF3M:111-114,141,153-154,204-205,398-402; Q2M:41-48,199-202,474-475 and F.conv1d (as im2col GEMM) at
+ * AF3M:343-344.  With AF3_EPI_SWIGLU, w holds gate/up rows interleaved in blocks of 128 (see af3_pack_gate_up)
+ * and out = silu(gate)*up with n_feat = intermediate size.  res_period > 0 adds resid[tok % res_period]. */
+int af3_gemm_bf16(void* stream, const void* x, int ldx, const void* w, int ldw, void* out, int ldo, int n_tok,
+                  int n_feat, int K, int flags, const void* bias, const void* resid, int ld_res, int res_period);
+
+/* gate [F,K], up [F,K] -> packed [2*ceil(F/128)*128, K]: per 128 features, 128 gate rows then 128 up rows. */
+int af3_pack_gate_up(void* stream, const void* gate, const void* up, void* packed, int F, int K);
+
+/* Log-mel front end; replaces WhisperFeatureExtractor._torch_extract_fbank_features ([O] WFE:135-164).
+ * wave fp32 [n_win, n_samples] (zero padded to 30 s by the caller as WFE:296 does), mel_filters fp32 [201,128]
+ * (from audio_utils.mel_filter_bank, WFE:95-103) with the first/last non-zero bin of each filter in mel_klo/khi,
+ * hann = torch.hann_window(400) (WFE:141), dft_table[n][k] = (cos, sin)(2 pi k n / 400) for n <= 200, k < 128.
+ * out fp32 [n_win, 128, n_samples/160]. */
+int af3_logmel(void* stream, const float* wave, int n_win, int n_samples, const float* hann /*[400]*/,
+               const float* dft_table /*[201][128] (cos,sin) pairs*/, const float* mel_filters /*[201][128]*/,
+               const int* mel_klo /*[128]*/, const int* mel_khi /*[128]*/, float* out, int* scratch_max /*[n_win]*/);
+
+/* conv stem helpers (AF3M:343-344 as GEMMs): im2col with k=3, pad=1.
+ * conv1: in [n_win, C, T] (fp32 or bf16 per in_is_f32) channel-major -> cols bf16 [n_win*T, 3*C], k index = kk*C+c
+ * conv2: in bf16 [n_win*T, C] channel-last, stride 2 -> cols bf16 [n_win*(T/2), 3*C] */
+int af3_im2col_conv1(void* stream, const void* in, int in_is_f32, void* cols, int n_win, int C, int T);
+int af3_im2col_conv2(void* stream, const void* in, void* cols, int n_win, int C, int T);
+
+/* LayerNorm over the last dim (AF3M:224,232 nn.LayerNorm eps 1e-5), bf16 in/out, fp32 statistics. */
+int af3_layernorm(void* stream, const void* x, void* y, const void* gamma, const void* beta, int rows, int dim,
+                  float eps);
+/* AvgPool1d(2,2) over time then LayerNorm (AF3M:364-366): x [n_win*T, dim] -> y [n_win*(T/2), dim]. */
+int af3_avgpool_layernorm(void* stream, const void* x, void* y, const void* gamma, const void* beta, int n_win, int T,
+                          int dim, float eps);
+/* Qwen2RMSNorm (Q2M:258-263): y = w * bf16(x * rsqrt(mean(x^2)+eps)); rows selected by optional row_idx. */
+int af3_rmsnorm(void* stream, const void* x, void* y, const void* weight, int rows, int dim, float eps,
+                const int* row_idx);
+
+/* Bidirectional / causal softmax attention on tcgen05 (replaces SDPA:40-104 as called from AF3M:170-181 and
+ * Q2M:227-238).  q rows come from a packed projection buffer: q[b, t, h*D + d] at q + (b*Tq + t)*ldq.
+ * k, v: element (b, hk, t, d) at k + ((b*Hkv + hk)*Tk_pitch + t)*ldk + d  when kv_layout = 1 (cache layout), or
+ * (b, t, hk*D + d) at k + (b*Tk + t)*ldk when kv_layout = 0 (packed projection buffer).
+ * kv_len[b] (may be NULL = Tk): keys >= kv_len[b] are masked (AF3M:337-351 key padding).
+ * kv_start[b] (may be NULL = 0): keys < kv_start[b] are masked (left padding, MASK:882).
+ * causal: key j visible to query i iff j <= i + (Tk - Tq).   out[b, t, h*D + d] at out + (b*Tq + t)*ldo. */
+int af3_attention(void* stream, const void* q, int ldq, const void* k, const void* v, int ldk, int kv_layout,
+                  int Tk_pitch, void* out, int ldo, int B, int H, int Hkv, int D, int Tq, int Tk, float scale,
+                  int causal, const int* kv_len, const int* kv_start);
+
+/* Rotary embedding + KV-cache append (Q2M:100-146, CACHE:119-120).  qkv bf16 [n_tok, (H+2*Hkv)*D] in place on q;
+ * k (rotated) and v are written to the cache [B, Hkv, Tmax, D] at position pos0 + t.  position id of token
+ * (b, t) = pos0 + t - kv_start[b]  (GEN:719-721 cumsum(attention_mask)-1; padded slots get position 1 as
+ * masked_fill_(mask == 0, 1) does).  pos0_dev (optional device int) overrides pos0 so a decode step can be replayed
+ * from a CUDA graph.  inv_freq fp32 [D/2] = Qwen2RotaryEmbedding.inv_freq (Q2M:86-89). */
+int af3_rope_kv_append(void* stream, void* qkv, void* k_cache, void* v_cache, int B, int T, int H, int Hkv, int D,
+                       int Tmax, int pos0, const int* pos0_dev, const int* kv_start, const float* inv_freq);
+
+/* Single-token attention over the KV cache (decode step; SDPA:40-104 with q_len = 1).  ctx_len is read from device
+ * memory so the launch can live in a CUDA graph.  q at qkv (packed [B, (H+2Hkv)*D]); out [B, H*D]. */
+int af3_decode_attention(void* stream, const void* qkv, const void* k_cache, const void* v_cache, void* out,
+                         float* scratch, int B, int H, int Hkv, int D, int Tmax, const int* ctx_len,
+                         const int* kv_start, float scale);
+size_t af3_decode_attention_scratch_bytes(int B, int H, int D);
+
+/* Token embedding gather + audio-row scatter (AF3M:557, 563-566 masked_scatter).
+ * ids int64 [n_tok]; audio rows taken in order from audio_embeds [n_win*frames, dim] keeping the first
+ * post_len[w] frames of each window (AF3M:469-473).  out bf16 [n_tok, dim].  counts[0] = #audio tokens,
+ * counts[1] = #valid audio rows (the caller raises if they differ, as masked_scatter would). */
+int af3_embed_scatter(void* stream, const int64_t* ids, int n_tok, const void* embed_table, int dim,
+                      int64_t audio_token_id, const void* audio_embeds, int n_win, int frames, const int* post_len,
+                      void* out, int* scratch_rows /*[n_tok]*/, int* counts /*[2]*/);
+
+/* Greedy step (GEN:2762-2800): argmax over fp32 logits [B, V] (first max index, like torch.argmax). */
+int af3_argmax(void* stream, const float* logits, int B, int V, int64_t* out_ids);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
