@@ -1,0 +1,575 @@
+"""B200-native Audio Flamingo 3 forward path behind the reference's PyTorch module surface.
+
+Mirrors (class roles, forward/generate/get_audio_features signatures, state_dict key names) the executable
+reference of this path, transformers 5.5.0 ([O]):
+    AudioFlamingo3Encoder                     [O] AF3M:265-379
+    AudioFlamingo3MultiModalProjector         [O] AF3M:382-402
+    Qwen2ForCausalLM / Qwen2Model             [O] Q2M:332-487
+    AudioFlamingo3ForConditionalGeneration    [O] AF3M:410-592 (+ greedy loop GEN:2658-2812)
+The nn.Module tree below only *holds* parameters under the reference's names (so `load_state_dict` of a reference
+checkpoint works unchanged); no nn.Module.forward of torch is ever executed.  All arithmetic runs in the hand-written
+sm_100a kernels of libaf3b200.so through audio_flamingo_b200.ops; this file is launch orchestration, buffer
+management (torch caching allocator, current CUDA stream) and CUDA-graph capture of the decode step.
+Compute dtype: bf16 parameters/activations, fp32 accumulation/statistics, fp32 logits -- same as running the
+reference with model.to(torch.bfloat16).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+from torch import nn
+
+from . import ops
+from ._lib import AF3Error
+
+bf16 = torch.bfloat16
+
+try:  # return types identical to the reference's when transformers is importable
+    from transformers.modeling_outputs import BaseModelOutputWithPooling, CausalLMOutputWithPast
+except Exception:  # pragma: no cover - minimal stand-ins with the same field names
+
+    @dataclass
+    class BaseModelOutputWithPooling:  # type: ignore
+        last_hidden_state: torch.Tensor = None
+        pooler_output: torch.Tensor = None
+
+    @dataclass
+    class CausalLMOutputWithPast:  # type: ignore
+        loss: Optional[torch.Tensor] = None
+        logits: torch.Tensor = None
+        past_key_values: object = None
+
+
+def _cfg_get(cfg, name, default=None):
+    return getattr(cfg, name, default) if not isinstance(cfg, dict) else cfg.get(name, default)
+
+
+# =====================================================================================================
+# parameter holders (names == reference state_dict keys)
+# =====================================================================================================
+class _EncAttn(nn.Module):
+    def __init__(self, d):
+        super().__init__()
+        self.k_proj = nn.Linear(d, d, bias=False)  # AF3M:111
+        self.v_proj = nn.Linear(d, d)
+        self.q_proj = nn.Linear(d, d)
+        self.out_proj = nn.Linear(d, d)
+
+
+class _EncLayer(nn.Module):
+    def __init__(self, d, ffn):
+        super().__init__()
+        self.self_attn = _EncAttn(d)
+        self.self_attn_layer_norm = nn.LayerNorm(d)
+        self.fc1 = nn.Linear(d, ffn)
+        self.fc2 = nn.Linear(ffn, d)
+        self.final_layer_norm = nn.LayerNorm(d)
+
+
+class AudioFlamingo3Encoder(nn.Module):
+    """AF-Whisper tower: conv stem -> +positions -> N pre-LN layers -> AvgPool(2) -> LayerNorm ([O] AF3M:265-379)."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        d = config.hidden_size
+        self.d_model, self.n_heads, self.ffn = d, config.num_attention_heads, config.intermediate_size
+        self.head_dim = d // self.n_heads
+        if self.head_dim not in (64, 128):
+            raise AF3Error("encoder head_dim must be 64 or 128 for the tcgen05 attention kernel")
+        self.num_mel_bins = config.num_mel_bins
+        self.max_source_positions = config.max_source_positions
+        if _cfg_get(config, "activation_function", "gelu") != "gelu" or _cfg_get(config, "scale_embedding", False):
+            raise AF3Error("only activation_function='gelu', scale_embedding=False (the AF3 configuration) is implemented")
+        self.conv1 = nn.Conv1d(self.num_mel_bins, d, kernel_size=3, padding=1)
+        self.conv2 = nn.Conv1d(d, d, kernel_size=3, stride=2, padding=1)
+        self.embed_positions = nn.Embedding(self.max_source_positions, d)
+        self.layers = nn.ModuleList([_EncLayer(d, self.ffn) for _ in range(config.num_hidden_layers)])
+        self.layer_norm = nn.LayerNorm(d)
+        self._packed = None
+
+    # ---- weight packing (once per load): conv weights to im2col order, fused QKV with the 1/sqrt(d) query scale folded
+    def pack_weights(self):
+        s = self.head_dim ** -0.5  # power of two for 64/128: folding it into W_q, b_q is exact in bf16 (AF3M:142)
+        P = {}
+        P["w1"] = self.conv1.weight.detach().permute(0, 2, 1).reshape(self.d_model, -1).contiguous()
+        P["w2"] = self.conv2.weight.detach().permute(0, 2, 1).reshape(self.d_model, -1).contiguous()
+        P["layers"] = []
+        for l in self.layers:
+            a = l.self_attn
+            wqkv = torch.cat([a.q_proj.weight.detach() * s, a.k_proj.weight.detach(), a.v_proj.weight.detach()], 0).contiguous()
+            bqkv = torch.cat([a.q_proj.bias.detach() * s, torch.zeros_like(a.q_proj.bias), a.v_proj.bias.detach()], 0).contiguous()
+            P["layers"].append((wqkv, bqkv))
+        self._packed = P
+
+    def _check_ready(self):
+        p = self.conv1.weight
+        if not p.is_cuda or p.dtype != bf16:
+            raise AF3Error("model must be on a CUDA device in bfloat16 (model.to('cuda', torch.bfloat16)); no CPU fallback")
+        if self._packed is None:
+            self.pack_weights()
+
+    def _get_feat_extract_output_lengths(self, input_lengths):
+        input_lengths = (input_lengths - 1) // 2 + 1
+        output_lengths = (input_lengths - 2) // 2 + 1
+        return input_lengths, output_lengths
+
+    @torch.no_grad()
+    def _encode(self, input_features, input_features_mask):
+        """-> ([W*T/2... pooled rows, d] bf16, W, pooled T)."""
+        self._check_ready()
+        P = self._packed
+        W, C, T = input_features.shape
+        if C != self.num_mel_bins:
+            raise ValueError(f"expected {self.num_mel_bins} mel bins, got {C}")
+        T2 = (T - 1) // 2 + 1
+        if T2 != self.max_source_positions:
+            raise ValueError(f"input_features must have {2 * self.max_source_positions} frames (got {T}); "
+                             "positions are added over the full window as in the reference (AF3M:348)")
+        d, H, hd = self.d_model, self.n_heads, self.head_dim
+        kv_len = None
+        if input_features_mask is not None:
+            lens = (input_features_mask.sum(-1).to(torch.int32) - 1) // 2 + 1        # AF3M:338-339
+            kv_len = lens.contiguous()
+        x_in = input_features.contiguous()
+        h1 = ops.linear(ops.im2col_conv1(x_in), P["w1"], self.conv1.bias, gelu=True)                    # AF3M:343
+        x = ops.linear(ops.im2col_conv2(h1, W, T), P["w2"], self.conv2.bias, gelu=True,
+                       resid=self.embed_positions.weight, res_period=T2)                               # AF3M:344-348
+        del h1
+        for l, (wqkv, bqkv) in zip(self.layers, P["layers"]):
+            y = ops.layernorm(x, l.self_attn_layer_norm.weight, l.self_attn_layer_norm.bias)
+            qkv = ops.linear(y, wqkv, bqkv)
+            a = torch.empty((W, T2, d), device=x.device, dtype=bf16)
+            ops.attention(qkv, qkv[:, d:], qkv[:, 2 * d:], a, B=W, H=H, Hkv=H, D=hd, Tq=T2, Tk=T2, scale=1.0, causal=False,
+                          kv_layout=0, ldq=3 * d, ldk=3 * d, kv_len=kv_len)                             # AF3M:170-181
+            ops.linear(a.view(W * T2, d), l.self_attn.out_proj.weight, l.self_attn.out_proj.bias, resid=x, out=x)
+            y = ops.layernorm(x, l.final_layer_norm.weight, l.final_layer_norm.bias, out=y)
+            f = ops.linear(y, l.fc1.weight, l.fc1.bias, gelu=True)
+            ops.linear(f, l.fc2.weight, l.fc2.bias, resid=x, out=x)
+        out = ops.avgpool_layernorm(x, W, T2, self.layer_norm.weight, self.layer_norm.bias)             # AF3M:364-366
+        return out, W, T2 // 2
+
+    def forward(self, input_features, input_features_mask=None, **kwargs):
+        out, W, Tp = self._encode(input_features, input_features_mask)
+        return BaseModelOutputWithPooling(last_hidden_state=out.view(W, Tp, self.d_model))
+
+
+class AudioFlamingo3MultiModalProjector(nn.Module):
+    """Linear -> GELU -> Linear ([O] AF3M:382-402)."""
+
+    def __init__(self, audio_hidden, text_hidden, bias=True):
+        super().__init__()
+        if not bias:
+            raise AF3Error("projector_bias=False is not implemented (AF3 uses bias, AF3C:102)")
+        self.linear_1 = nn.Linear(audio_hidden, text_hidden)
+        self.linear_2 = nn.Linear(text_hidden, text_hidden)
+
+    @torch.no_grad()
+    def forward(self, audio_features):
+        shp = audio_features.shape
+        x = audio_features.reshape(-1, shp[-1])
+        h = ops.linear(x, self.linear_1.weight, self.linear_1.bias, gelu=True)
+        y = ops.linear(h, self.linear_2.weight, self.linear_2.bias)
+        return y.view(*shp[:-1], y.shape[-1])
+
+
+class _DecAttn(nn.Module):
+    def __init__(self, hid, H, Hkv, D):
+        super().__init__()
+        self.q_proj = nn.Linear(hid, H * D, bias=True)
+        self.k_proj = nn.Linear(hid, Hkv * D, bias=True)
+        self.v_proj = nn.Linear(hid, Hkv * D, bias=True)
+        self.o_proj = nn.Linear(H * D, hid, bias=False)
+
+
+class _DecMLP(nn.Module):
+    def __init__(self, hid, inter):
+        super().__init__()
+        self.gate_proj = nn.Linear(hid, inter, bias=False)
+        self.up_proj = nn.Linear(hid, inter, bias=False)
+        self.down_proj = nn.Linear(inter, hid, bias=False)
+
+
+class _RMSNormW(nn.Module):
+    def __init__(self, hid):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(hid))
+
+
+class _DecLayer(nn.Module):
+    def __init__(self, hid, inter, H, Hkv, D):
+        super().__init__()
+        self.self_attn = _DecAttn(hid, H, Hkv, D)
+        self.mlp = _DecMLP(hid, inter)
+        self.input_layernorm = _RMSNormW(hid)
+        self.post_attention_layernorm = _RMSNormW(hid)
+
+
+class _Qwen2Model(nn.Module):
+    def __init__(self, tc):
+        super().__init__()
+        hid, H, Hkv = tc.hidden_size, tc.num_attention_heads, tc.num_key_value_heads
+        D = _cfg_get(tc, "head_dim", None) or hid // H
+        self.embed_tokens = nn.Embedding(tc.vocab_size, hid)
+        self.layers = nn.ModuleList([_DecLayer(hid, tc.intermediate_size, H, Hkv, D) for _ in range(tc.num_hidden_layers)])
+        self.norm = _RMSNormW(hid)
+
+
+class AF3KVCache:
+    """Pre-allocated KV cache [layers][B, Hkv, Tmax, D] (replaces DynamicCache's grow-by-cat, [O] CACHE:88-121).
+    `length` = number of filled slots (host int); `pos_dev`/`ctx_dev` mirror it on the device for graph replay."""
+
+    def __init__(self, n_layers, B, Hkv, Tmax, D, device):
+        self.k = torch.empty((n_layers, B, Hkv, Tmax, D), device=device, dtype=bf16)
+        self.v = torch.empty_like(self.k)
+        self.B, self.Tmax = B, Tmax
+        self.length = 0
+        self.kv_start = None  # int32 [B]: left-padding length per sequence
+        self.pos_dev = torch.zeros((1,), device=device, dtype=torch.int32)
+        self.ctx_dev = torch.ones((1,), device=device, dtype=torch.int32)
+
+    def get_seq_length(self, layer_idx=0):
+        return self.length
+
+
+class Qwen2ForCausalLM(nn.Module):
+    """Decoder ([O] Q2M:332-487) on sm_100a kernels: RMSNorm, fused QKV GEMM (+bias), RoPE + in-place KV append,
+    tcgen05 causal GQA attention (prefill) / split-KV decode attention, o GEMM (+residual), fused SwiGLU GEMM,
+    down GEMM (+residual), final norm, LM head to fp32 logits."""
+
+    def __init__(self, tc):
+        super().__init__()
+        self.config = tc
+        self.hid, self.H, self.Hkv = tc.hidden_size, tc.num_attention_heads, tc.num_key_value_heads
+        self.D = _cfg_get(tc, "head_dim", None) or self.hid // self.H
+        if self.D != 128:
+            raise AF3Error("decoder head_dim must be 128 (Qwen2.5-7B geometry) for the attention kernels")
+        if _cfg_get(tc, "hidden_act", "silu") != "silu":
+            raise AF3Error("only hidden_act='silu' is implemented")
+        self.inter, self.vocab, self.eps = tc.intermediate_size, tc.vocab_size, tc.rms_norm_eps
+        rp = _cfg_get(tc, "rope_parameters", None) or {}
+        self.rope_theta = rp.get("rope_theta", _cfg_get(tc, "rope_theta", 10000.0))
+        if rp.get("rope_type", "default") != "default":
+            raise AF3Error("only default RoPE is implemented")
+        self.model = _Qwen2Model(tc)
+        self.lm_head = nn.Linear(self.hid, self.vocab, bias=False)
+        self._packed = None
+        self._inv_freq = None
+
+    def pack_weights(self):
+        P = []
+        for l in self.model.layers:
+            a, m = l.self_attn, l.mlp
+            wqkv = torch.cat([a.q_proj.weight.detach(), a.k_proj.weight.detach(), a.v_proj.weight.detach()], 0).contiguous()
+            bqkv = torch.cat([a.q_proj.bias.detach(), a.k_proj.bias.detach(), a.v_proj.bias.detach()], 0).contiguous()
+            wgu = ops.pack_gate_up(m.gate_proj.weight.detach().contiguous(), m.up_proj.weight.detach().contiguous())
+            P.append((wqkv, bqkv, wgu))
+        self._packed = P
+        # Qwen2RotaryEmbedding.compute_default_rope_parameters, evaluated on the CPU like the reference (Q2M:86-89)
+        inv = 1.0 / (self.rope_theta ** (torch.arange(0, self.D, 2, dtype=torch.int64).to(dtype=torch.float) / self.D))
+        self._inv_freq = inv.to(self.lm_head.weight.device)
+
+    def _check_ready(self):
+        p = self.lm_head.weight
+        if not p.is_cuda or p.dtype != bf16:
+            raise AF3Error("model must be on a CUDA device in bfloat16 (model.to('cuda', torch.bfloat16)); no CPU fallback")
+        if self._packed is None:
+            self.pack_weights()
+
+    def new_cache(self, B, Tmax):
+        dev = self.lm_head.weight.device
+        return AF3KVCache(len(self.model.layers), B, self.Hkv, Tmax, self.D, dev)
+
+    # ------------------------------------------------------------------ core stacks
+    def _layers(self, h, B, T, cache: AF3KVCache, decode: bool, scratch=None):
+        """h [B*T, hid] residual stream, updated in place and returned."""
+        H, Hkv, D = self.H, self.Hkv, self.D
+        pos0 = cache.length
+        for li, (l, (wqkv, bqkv, wgu)) in enumerate(zip(self.model.layers, self._packed)):
+            y = ops.rmsnorm(h, l.input_layernorm.weight, self.eps)
+            qkv = ops.linear(y, wqkv, bqkv)
+            kc, vc = cache.k[li], cache.v[li]
+            a = torch.empty((B * T, H * D), device=h.device, dtype=bf16)
+            if decode:
+                ops.rope_kv_append(qkv, kc, vc, B=B, T=1, H=H, Hkv=Hkv, D=D, pos0=0, inv_freq=self._inv_freq,
+                                   kv_start=cache.kv_start, pos0_dev=cache.pos_dev)
+                ops.decode_attention(qkv, kc, vc, a, scratch, B=B, H=H, Hkv=Hkv, D=D, ctx_len=cache.ctx_dev,
+                                     kv_start=cache.kv_start, scale=D ** -0.5)
+            else:
+                ops.rope_kv_append(qkv, kc, vc, B=B, T=T, H=H, Hkv=Hkv, D=D, pos0=pos0, inv_freq=self._inv_freq,
+                                   kv_start=cache.kv_start)
+                ops.attention(qkv, kc, vc, a.view(B, T, H * D), B=B, H=H, Hkv=Hkv, D=D, Tq=T, Tk=pos0 + T, scale=D ** -0.5,
+                              causal=True, kv_layout=1, Tk_pitch=cache.Tmax, ldq=(H + 2 * Hkv) * D, ldk=D,
+                              kv_start=cache.kv_start)
+            ops.linear(a, l.self_attn.o_proj.weight, resid=h, out=h)
+            y = ops.rmsnorm(h, l.post_attention_layernorm.weight, self.eps, out=y)
+            g = ops.swiglu_linear(y, wgu, self.inter)
+            ops.linear(g, l.mlp.down_proj.weight, resid=h, out=h)
+        return h
+
+    def _head(self, h, row_idx=None):
+        y = ops.rmsnorm(h, self.model.norm.weight, self.eps, row_idx=row_idx)
+        return ops.linear(y, self.lm_head.weight, out_f32=True)
+
+    @torch.no_grad()
+    def prefill(self, inputs_embeds, kv_start, cache: AF3KVCache, logits_to_keep=1):
+        """inputs_embeds [B,S,hid] bf16 (consumed in place), kv_start int32 [B]. -> fp32 logits [B, keep|S, V]."""
+        self._check_ready()
+        B, S, _ = inputs_embeds.shape
+        if cache.length + S > cache.Tmax:
+            raise AF3Error("KV cache too small for this prompt")
+        cache.kv_start = kv_start
+        h = self._layers(inputs_embeds.view(B * S, self.hid), B, S, cache, decode=False)
+        cache.length += S
+        cache.pos_dev.fill_(cache.length)
+        cache.ctx_dev.fill_(cache.length + 1)
+        if logits_to_keep == 0:
+            return self._head(h).view(B, S, self.vocab)
+        if logits_to_keep != 1:
+            raise AF3Error("logits_to_keep must be 0 (all positions) or 1 (last position)")
+        last = torch.arange(B, device=h.device, dtype=torch.int32) * S + (S - 1)
+        return self._head(h, last).view(B, 1, self.vocab)
+
+    @torch.no_grad()
+    def decode_step(self, token_embeds, cache: AF3KVCache, scratch):
+        """One q_len = 1 step: token_embeds [B, hid] (in place) -> fp32 logits [B, V]; appends at cache.pos_dev.
+        Graph-capturable: positions / context length are read from device memory and advanced on the device."""
+        B = token_embeds.shape[0]
+        h = self._layers(token_embeds, B, 1, cache, decode=True, scratch=scratch)
+        logits = self._head(h)
+        cache.pos_dev.add_(1)
+        cache.ctx_dev.add_(1)
+        return logits
+
+
+# =====================================================================================================
+# the drop-in top-level model
+# =====================================================================================================
+class AudioFlamingo3ForConditionalGeneration(nn.Module):
+    """Drop-in for the reference class of the same name ([O] AF3M:410-592) on its audio->text inference path."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.vocab_size = config.text_config.vocab_size
+        with torch.device("meta"):
+            self.audio_tower = AudioFlamingo3Encoder(config.audio_config)
+            self.language_model = Qwen2ForCausalLM(config.text_config)
+            self.multi_modal_projector = AudioFlamingo3MultiModalProjector(
+                config.audio_config.hidden_size, config.text_config.hidden_size, _cfg_get(config, "projector_bias", True))
+        if _cfg_get(config, "projector_hidden_act", "gelu") != "gelu":
+            raise AF3Error("only projector_hidden_act='gelu' is implemented")
+        self._graph = None
+        self.stage_events = None  # bench instrumentation: when a list, (name, cuda event) is appended at stage boundaries
+
+    def _mark(self, name):
+        if self.stage_events is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.stage_events.append((name, ev))
+
+    # ---- construction from the reference model / a reference state_dict
+    @classmethod
+    def from_reference(cls, ref_model, device="cuda"):
+        """Build from an instantiated reference model (weights are copied, cast to bf16)."""
+        m = cls(ref_model.config)
+        m.load_reference_state_dict(ref_model.state_dict(), device=device)
+        return m
+
+    def load_reference_state_dict(self, sd, device="cuda"):
+        self.to_empty(device=device)
+        self.to(bf16)
+        own = self.state_dict()
+        missing = [k for k in own if k not in sd]
+        unexpected = [k for k in sd if k not in own]
+        if missing or unexpected:
+            raise AF3Error(f"state_dict mismatch: missing {missing[:4]}..., unexpected {unexpected[:4]}...")
+        with torch.no_grad():
+            for k, v in own.items():
+                v.copy_(sd[k].to(device=v.device, dtype=bf16))
+        self.audio_tower._packed = None
+        self.language_model._packed = None
+        self._graph = None
+        return self
+
+    def get_input_embeddings(self):
+        return self.language_model.model.embed_tokens
+
+    def get_output_embeddings(self):
+        return self.language_model.lm_head
+
+    # ---- audio branch
+    @torch.no_grad()
+    def get_audio_features(self, input_features, input_features_mask, **kwargs):
+        """[O] AF3M:447-475: tower -> projector -> keep the first post_len frames of every window."""
+        enc, W, Tp = self.audio_tower._encode(input_features, input_features_mask)
+        emb = self.multi_modal_projector(enc)                                   # [W*Tp, text_hidden]
+        lens = input_features_mask.sum(-1).to(torch.long)
+        _, post = self.audio_tower._get_feat_extract_output_lengths(lens)
+        valid = torch.arange(Tp, device=emb.device)[None, :] < post[:, None]
+        out = BaseModelOutputWithPooling(last_hidden_state=enc.view(W, Tp, -1))
+        out.pooler_output = emb.view(W, Tp, -1)[valid]
+        return out
+
+    def _audio_embeds_raw(self, input_features, input_features_mask):
+        enc, W, Tp = self.audio_tower._encode(input_features, input_features_mask)
+        emb = self.multi_modal_projector(enc)
+        lens = input_features_mask.sum(-1).to(torch.int32)
+        post = (((lens - 1) // 2 + 1) - 2) // 2 + 1
+        return emb, W, Tp, post.to(torch.int32).contiguous()
+
+    @staticmethod
+    def _left_pad_starts(attention_mask, B, S, device):
+        if attention_mask is None:
+            return torch.zeros((B,), device=device, dtype=torch.int32)
+        am = attention_mask.to(device)
+        n_valid = am.sum(-1)
+        # the kernels implement the reference's left padding (AF3P:44-47): mask must be 0...01...1
+        expect = torch.arange(S, device=device)[None, :] >= (S - n_valid)[:, None]
+        if not torch.equal(am.bool(), expect):
+            raise AF3Error("attention_mask must be left padded (zeros then ones), as the AF3 processor produces")
+        return (S - n_valid).to(torch.int32).contiguous()
+
+    @torch.no_grad()
+    def _prompt_embeds(self, input_ids, input_features, input_features_mask):
+        B, S = input_ids.shape
+        dev = self.language_model.lm_head.weight.device
+        ids = input_ids.to(dev).reshape(-1).contiguous()
+        table = self.language_model.model.embed_tokens.weight
+        if input_features is not None:
+            emb, W, Tp, post = self._audio_embeds_raw(input_features.to(dev), input_features_mask.to(dev))
+            x, counts = ops.embed_scatter(ids, table, self.config.audio_token_id, emb, W, Tp, post)
+            n_tok, n_feat = counts.tolist()
+            if n_tok != n_feat:  # masked_scatter would fail the same way (AF3M:564)
+                raise ValueError(f"Audio features and audio tokens do not match: tokens {n_tok}, features {n_feat}")
+        else:
+            x, _ = ops.embed_scatter(ids, table, -1, None, 0, 1, None)
+        return x.view(B, S, -1)
+
+    # ---- forward ([O] AF3M:479-578)
+    @torch.no_grad()
+    def forward(self, input_ids=None, input_features=None, input_features_mask=None, attention_mask=None,
+                position_ids=None, past_key_values=None, inputs_embeds=None, labels=None, use_cache=None,
+                logits_to_keep=0, **kwargs):
+        if labels is not None:
+            raise AF3Error("training (labels) is out of scope of the inference hot path")
+        if position_ids is not None:
+            raise AF3Error("explicit position_ids are not supported; they are derived from the left-padded attention_mask")
+        self.language_model._check_ready()
+        lm = self.language_model
+        dev = lm.lm_head.weight.device
+        if past_key_values is not None and past_key_values.length > 0:
+            # cached continuation: only the new token(s) are passed (AF3M:580-592: no audio after the first iteration)
+            if input_ids is None or input_ids.shape[1] != 1:
+                raise AF3Error("cached forward expects exactly one new token per sequence")
+            B = input_ids.shape[0]
+            x, _ = ops.embed_scatter(input_ids.to(dev).reshape(-1).contiguous(), lm.model.embed_tokens.weight, -1, None, 0, 1, None)
+            scratch = ops.decode_attention_scratch(B, lm.H, lm.D, dev)
+            logits = lm.decode_step(x, past_key_values, scratch)
+            past_key_values.length += 1
+            return CausalLMOutputWithPast(logits=logits.view(B, 1, -1), past_key_values=past_key_values)
+        if inputs_embeds is None:
+            inputs_embeds = self._prompt_embeds(input_ids, input_features, input_features_mask)
+        else:
+            inputs_embeds = inputs_embeds.to(dev, bf16).clone()
+        B, S, _ = inputs_embeds.shape
+        kv_start = self._left_pad_starts(attention_mask, B, S, dev)
+        cache = past_key_values if past_key_values is not None else lm.new_cache(B, max(S, 1) + (kwargs.get("reserve_tokens", 0)))
+        logits = lm.prefill(inputs_embeds, kv_start, cache, logits_to_keep=logits_to_keep)
+        return CausalLMOutputWithPast(logits=logits, past_key_values=cache if (use_cache or past_key_values is not None) else None)
+
+    __call__ = forward  # nn.Module.__call__ hooks are not needed on the inference path
+
+    # ---- greedy generation ([O] GEN:2131 generate -> GEN:2658 _sample with do_sample=False)
+    @torch.no_grad()
+    def generate(self, input_ids=None, attention_mask=None, input_features=None, input_features_mask=None,
+                 max_new_tokens=20, do_sample=False, eos_token_id=None, pad_token_id=None, use_cuda_graph=True,
+                 return_logits=False, **kwargs):
+        if do_sample:
+            raise AF3Error("only greedy decoding (do_sample=False) is implemented")
+        lm = self.language_model
+        lm._check_ready()
+        dev = lm.lm_head.weight.device
+        B, S = input_ids.shape
+        self._mark("start")
+        x = self._prompt_embeds(input_ids, input_features, input_features_mask)
+        self._mark("audio_done")
+        kv_start = self._left_pad_starts(attention_mask, B, S, dev)
+        cache = lm.new_cache(B, S + max_new_tokens)
+        logits = lm.prefill(x, kv_start, cache, logits_to_keep=1).view(B, -1)           # GEN:3724 _prefill
+        self._mark("prefill_done")
+        out = torch.empty((B, S + max_new_tokens), device=dev, dtype=torch.int64)
+        out[:, :S] = input_ids.to(dev)
+        eos = None
+        if eos_token_id is not None:
+            eos = torch.as_tensor([eos_token_id] if isinstance(eos_token_id, int) else list(eos_token_id), device=dev)
+            if pad_token_id is None:
+                pad_token_id = int(eos[0])
+            unfinished = torch.ones((B,), device=dev, dtype=torch.int64)
+        kept_logits = [logits.clone()] if return_logits else None
+        next_ids = ops.argmax(logits)                                                   # GEN:2793
+        step_fn = self._decode_runner(B, cache, use_cuda_graph and max_new_tokens > 2)
+        n_done = max_new_tokens
+        for i in range(max_new_tokens):
+            if eos is not None:
+                next_ids = next_ids * unfinished + pad_token_id * (1 - unfinished)      # GEN:2797
+            out[:, S + i] = next_ids
+            if eos is not None:
+                unfinished = unfinished & ~torch.isin(next_ids, eos)
+                if int(unfinished.max()) == 0:                                          # GEN:2805 (one sync per step)
+                    n_done = i + 1
+                    break
+            if i + 1 == max_new_tokens:
+                break
+            logits = step_fn(next_ids)
+            cache.length += 1
+            if return_logits:
+                kept_logits.append(logits.clone())
+            next_ids = ops.argmax(logits)
+        result = out[:, : S + n_done]
+        self._mark("decode_done")
+        if return_logits:
+            return result, torch.stack(kept_logits, 1)
+        return result
+
+    def _decode_runner(self, B, cache, use_graph):
+        """Returns step(next_ids[int64 B]) -> fp32 logits [B, V].  With use_graph the whole step (embedding gather, 28
+        layers, head) is captured once in a CUDA graph and replayed; positions advance on the device."""
+        lm = self.language_model
+        dev = lm.lm_head.weight.device
+        table = lm.model.embed_tokens.weight
+        scratch = ops.decode_attention_scratch(B, lm.H, lm.D, dev)
+        ids_buf = torch.zeros((B,), device=dev, dtype=torch.int64)
+
+        def eager(next_ids):
+            x, _ = ops.embed_scatter(next_ids, table, -1, None, 0, 1, None)
+            return lm.decode_step(x, cache, scratch)
+
+        if not use_graph:
+            return eager
+        state = {"graph": None, "logits": None, "warm": 0}
+
+        def step(next_ids):
+            ids_buf.copy_(next_ids)
+            if state["graph"] is None:
+                if state["warm"] < 1:  # first step eagerly (configures kernels, warms the allocator)
+                    state["warm"] += 1
+                    return eager(ids_buf)
+                g = torch.cuda.CUDAGraph()
+                torch.cuda.synchronize()
+                prof, ops.PROFILE = ops.PROFILE, None  # timing events cannot be recorded inside a capture
+                n0 = ops.LAUNCHES
+                with torch.cuda.graph(g):
+                    state["logits"] = eager(ids_buf)
+                state["launches"] = ops.LAUNCHES - n0
+                ops.LAUNCHES = n0  # capture launched nothing; replays are counted below
+                ops.PROFILE = prof
+                state["graph"] = g
+            state["graph"].replay()  # (capture does not execute: the first replay runs this token's step)
+            ops._count(state["launches"])
+            return state["logits"]
+
+        return step

@@ -15,6 +15,35 @@ from ._lib import EPI_BIAS, EPI_F32OUT, EPI_GELU, EPI_RESID, EPI_SWIGLU, check, 
 
 bf16 = torch.bfloat16
 
+# ---- instrumentation used by bench.py (counts are claims about OUR kernels; see DESIGN.md "measurement")
+LAUNCHES = 0      # CUDA kernels launched through the C ABI since the last reset (graph replays add their captured count)
+PROFILE = None    # when a dict: (kind, n_tok, n_feat, K, flags) -> list of (cuda start event, end event)
+
+
+def _count(n: int) -> None:
+    global LAUNCHES
+    LAUNCHES += n
+
+
+class _Timed:
+    """Brackets one C-ABI call with CUDA events on the current stream when PROFILE is enabled."""
+
+    def __init__(self, key):
+        self.key = key if PROFILE is not None else None
+
+    def __enter__(self):
+        if self.key is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.key is not None:
+            self.e1.record()
+            PROFILE.setdefault(self.key, []).append((self.e0, self.e1))
+        return False
+
 
 def _req(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
     if not t.is_cuda:
@@ -46,11 +75,13 @@ def linear(x, w, bias=None, *, gelu=False, resid=None, res_period=0, out=None, o
         flags |= EPI_F32OUT
     if out is None:
         out = torch.empty((n_tok, n_feat), device=x.device, dtype=torch.float32 if out_f32 else bf16)
-    check(
-        lib.af3_gemm_bf16(stream_ptr(), ptr(x), x.stride(0), ptr(w), w.stride(0), ptr(out), out.stride(0), n_tok, n_feat,
-                          K, flags, ptr(bias), ptr(resid), resid.stride(0) if resid is not None else 0, res_period),
-        "af3_gemm_bf16",
-    )
+    with _Timed(("gemm", n_tok, n_feat, K, flags)):
+        check(
+            lib.af3_gemm_bf16(stream_ptr(), ptr(x), x.stride(0), ptr(w), w.stride(0), ptr(out), out.stride(0), n_tok, n_feat,
+                              K, flags, ptr(bias), ptr(resid), resid.stride(0) if resid is not None else 0, res_period),
+            "af3_gemm_bf16",
+        )
+    _count(1)
     return out
 
 
@@ -60,6 +91,7 @@ def pack_gate_up(gate, up):
     F, K = gate.shape
     packed = torch.empty((2 * ((F + 127) // 128) * 128, K), device=gate.device, dtype=bf16)
     check(lib.af3_pack_gate_up(stream_ptr(), ptr(gate), ptr(up), ptr(packed), F, K), "af3_pack_gate_up")
+    _count(1)
     return packed
 
 
@@ -70,11 +102,13 @@ def swiglu_linear(x, w_packed, n_feat, out=None):
     n_tok, K = x.shape
     if out is None:
         out = torch.empty((n_tok, n_feat), device=x.device, dtype=bf16)
-    check(
-        lib.af3_gemm_bf16(stream_ptr(), ptr(x), x.stride(0), ptr(w_packed), w_packed.stride(0), ptr(out), out.stride(0),
-                          n_tok, n_feat, K, EPI_SWIGLU, None, None, 0, 0),
-        "af3_gemm_bf16(swiglu)",
-    )
+    with _Timed(("gemm", n_tok, n_feat, K, EPI_SWIGLU)):
+        check(
+            lib.af3_gemm_bf16(stream_ptr(), ptr(x), x.stride(0), ptr(w_packed), w_packed.stride(0), ptr(out), out.stride(0),
+                              n_tok, n_feat, K, EPI_SWIGLU, None, None, 0, 0),
+            "af3_gemm_bf16(swiglu)",
+        )
+    _count(1)
     return out
 
 
@@ -108,11 +142,13 @@ def logmel(wave, tables: LogMelTables):
     n_win, n_samples = wave.shape
     out = torch.empty((n_win, 128, n_samples // 160), device=wave.device, dtype=torch.float32)
     scratch = torch.empty((n_win,), device=wave.device, dtype=torch.int32)
-    check(
-        lib.af3_logmel(stream_ptr(), ptr(wave), n_win, n_samples, ptr(tables.hann), ptr(tables.table), ptr(tables.filters),
-                       ptr(tables.klo), ptr(tables.khi), ptr(out), ptr(scratch)),
-        "af3_logmel",
-    )
+    with _Timed(("logmel", n_win, n_samples, 0, 0)):
+        check(
+            lib.af3_logmel(stream_ptr(), ptr(wave), n_win, n_samples, ptr(tables.hann), ptr(tables.table), ptr(tables.filters),
+                           ptr(tables.klo), ptr(tables.khi), ptr(out), ptr(scratch)),
+            "af3_logmel",
+        )
+    _count(3)
     return out
 
 
@@ -126,6 +162,7 @@ def im2col_conv1(x):
     n_win, Cc, T = x.shape
     cols = torch.empty((n_win * T, 3 * Cc), device=x.device, dtype=bf16)
     check(lib.af3_im2col_conv1(stream_ptr(), ptr(x), int(x.dtype == torch.float32), ptr(cols), n_win, Cc, T), "af3_im2col_conv1")
+    _count(1)
     return cols
 
 
@@ -137,6 +174,7 @@ def im2col_conv2(h, n_win, T):
     T_out = (T - 1) // 2 + 1
     cols = torch.empty((n_win * T_out, 3 * Cc), device=h.device, dtype=bf16)
     check(lib.af3_im2col_conv2(stream_ptr(), ptr(h), ptr(cols), n_win, Cc, T), "af3_im2col_conv2")
+    _count(1)
     return cols
 
 
@@ -148,6 +186,7 @@ def layernorm(x, gamma, beta, eps=1e-5, out=None):
     if out is None:
         out = torch.empty_like(x)
     check(lib.af3_layernorm(stream_ptr(), ptr(x), ptr(out), ptr(gamma), ptr(beta), rows, dim, eps), "af3_layernorm")
+    _count(1)
     return out
 
 
@@ -157,6 +196,7 @@ def avgpool_layernorm(x, n_win, T, gamma, beta, eps=1e-5):
     dim = x.shape[1]
     out = torch.empty((n_win * (T // 2), dim), device=x.device, dtype=bf16)
     check(lib.af3_avgpool_layernorm(stream_ptr(), ptr(x), ptr(out), ptr(gamma), ptr(beta), n_win, T, dim, eps), "af3_avgpool_layernorm")
+    _count(1)
     return out
 
 
@@ -168,6 +208,7 @@ def rmsnorm(x, weight, eps=1e-6, row_idx=None, out=None):
     if out is None:
         out = torch.empty((rows, dim), device=x.device, dtype=bf16)
     check(lib.af3_rmsnorm(stream_ptr(), ptr(x), ptr(out), ptr(weight), rows, dim, eps, ptr(row_idx)), "af3_rmsnorm")
+    _count(1)
     return out
 
 
@@ -175,11 +216,13 @@ def rmsnorm(x, weight, eps=1e-6, row_idx=None, out=None):
 def attention(q, k, v, out, *, B, H, Hkv, D, Tq, Tk, scale, causal, kv_layout=0, Tk_pitch=0, ldq=None, ldk=None,
               kv_len=None, kv_start=None):
     lib = _lib.load()
-    check(
-        lib.af3_attention(stream_ptr(), ptr(q), ldq, ptr(k), ptr(v), ldk, kv_layout, Tk_pitch, ptr(out), out.stride(-2),
-                          B, H, Hkv, D, Tq, Tk, float(scale), int(causal), ptr(kv_len), ptr(kv_start)),
-        "af3_attention",
-    )
+    with _Timed(("attention", B * H, Tq, Tk, D * 2 + int(causal))):
+        check(
+            lib.af3_attention(stream_ptr(), ptr(q), ldq, ptr(k), ptr(v), ldk, kv_layout, Tk_pitch, ptr(out), out.stride(-2),
+                              B, H, Hkv, D, Tq, Tk, float(scale), int(causal), ptr(kv_len), ptr(kv_start)),
+            "af3_attention",
+        )
+    _count(1)
     return out
 
 
@@ -191,6 +234,7 @@ def rope_kv_append(qkv, k_cache, v_cache, *, B, T, H, Hkv, D, pos0, inv_freq, kv
                                ptr(kv_start), ptr(inv_freq)),
         "af3_rope_kv_append",
     )
+    _count(1)
 
 
 def decode_attention(qkv, k_cache, v_cache, out, scratch, *, B, H, Hkv, D, ctx_len, kv_start, scale):
@@ -201,6 +245,7 @@ def decode_attention(qkv, k_cache, v_cache, out, scratch, *, B, H, Hkv, D, ctx_l
                                  Tmax, ptr(ctx_len), ptr(kv_start), float(scale)),
         "af3_decode_attention",
     )
+    _count(2)
     return out
 
 
@@ -229,6 +274,7 @@ def embed_scatter(ids, table, audio_token_id, audio_embeds, n_win, frames, post_
                               frames, ptr(post_len), ptr(out), ptr(scratch), ptr(counts)),
         "af3_embed_scatter",
     )
+    _count(2)
     return out, counts
 
 
@@ -239,4 +285,5 @@ def argmax(logits, out=None):
     if out is None:
         out = torch.empty((B,), device=logits.device, dtype=torch.int64)
     check(lib.af3_argmax(stream_ptr(), ptr(logits), B, V, ptr(out)), "af3_argmax")
+    _count(1)
     return out

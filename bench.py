@@ -1,0 +1,484 @@
+#!/usr/bin/env python
+"""bench.py -- AF3-7B audio->text hot path on B200 (driver contract; see DESIGN.md "Measurement").
+
+Workload (BASELINE.json configs[1]): AF3-7B, batch 32 x 30 s clips per GPU, greedy 128-token decode.
+One "step" = one pass of the whole path over one batch of synthetic audio:
+    log-mel -> AF-Whisper encoder -> projector -> prompt embedding scatter -> Qwen2 prefill -> 127 cached decode steps
+`value`  = generated tokens/s for the whole job with the waveform batch already resident in HBM.
+`e2e`    = the same through the public API from HOST buffers: pinned-host waveforms + prompt ids are copied to the
+           device and the generated ids are read back inside the timed region.
+Also reported (BASELINE's metric pair): audio_s_per_s (mel+encoder+projector) and decode_tok_s (cached steps only),
+a roofline object for the dominant kernel, and the reference's CPU path timed on this box's host cores.
+
+`--impl reference` times the reference's own implementation of the path (unmodified Hugging Face transformers classes,
+see oracle/af3_oracle.py) on the host cores, on bounded samples of the same workload.
+
+Multi-GPU (torchrun, one rank per GPU): weights replicated, every rank runs its own 32-clip batch (weak scaling),
+the only collective is the final all-gather of the generated ids (NCCL).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WORKLOAD = "AF3-7B batch-32 x 30s clips, greedy 128-token decode"
+METRIC = "generated tokens/s, audio->text end to end (log-mel + AF-Whisper encode + prefill + greedy decode), AF3-7B"
+B_PER_GPU, CLIP_S, NEW_TOKENS = 32, 30.0, 128
+N_PRE, N_POST = 5, 25
+
+
+# ----------------------------------------------------------------------------------------------------- helpers
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (profiling recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])), mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "MEASURED_PEAKS.json (of measured)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "B200_PROFILING.md fallback (of fallback)"}
+
+
+def af3_config():
+    from transformers import AudioFlamingo3Config
+
+    text = dict(vocab_size=152064, hidden_size=3584, intermediate_size=18944, num_hidden_layers=28, num_attention_heads=28,
+                num_key_value_heads=4, max_position_embeddings=32768, rms_norm_eps=1e-6, tie_word_embeddings=False,
+                rope_parameters={"rope_type": "default", "rope_theta": 1000000.0})
+    return AudioFlamingo3Config(audio_config=dict(), text_config=text, audio_token_id=151669)
+
+
+def synth_batch(B: int, seed: int):
+    """Seeded synthetic batch: 30 s noise clips and [5 text] + 750 x <sound> + [25 text] prompts."""
+    rs = np.random.RandomState(seed)
+    wave = (rs.randn(B, int(CLIP_S * 16000)) * 0.1).astype(np.float32)
+    tok = 750
+    ids = np.empty((B, N_PRE + tok + N_POST), dtype=np.int64)
+    ids[:, :N_PRE] = rs.randint(1, 151643, size=(B, N_PRE))
+    ids[:, N_PRE:N_PRE + tok] = 151669
+    ids[:, N_PRE + tok:] = rs.randint(1, 151643, size=(B, N_POST))
+    return wave, ids
+
+
+def init_synthetic_weights_(model, seed: int):
+    """Random-init weights of the AF3-7B architecture directly on the GPU (no checkpoint exists offline):
+    N(0, 0.02) matrices / embeddings, zero biases, unit norm gains -- the reference's default init family."""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if name.endswith("bias"):
+                p.zero_()
+            elif "norm" in name and name.endswith("weight"):
+                p.fill_(1.0)
+            else:
+                p.normal_(0.0, 0.02, generator=g)
+
+
+# ----------------------------------------------------------------------------------------------------- ours
+def run_ours(args):
+    rank, world, local = dist_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    from audio_flamingo_b200 import AF3FeatureExtractor, AudioFlamingo3ForConditionalGeneration, ops
+    from audio_flamingo_b200.sharding import gather_tokens
+
+    cfg = af3_config()
+    model = AudioFlamingo3ForConditionalGeneration(cfg)
+    model.to_empty(device=dev)
+    model.to(torch.bfloat16)
+    init_synthetic_weights_(model, seed=0)
+    fe = AF3FeatureExtractor(dev)
+    B = B_PER_GPU
+    wave_np, ids_np = synth_batch(B, seed=1000 + rank)
+    wave_host = torch.from_numpy(wave_np).pin_memory()
+    ids_host = torch.from_numpy(ids_np).pin_memory()
+    wave_dev = wave_host.to(dev)
+    ids_dev = ids_host.to(dev)
+    mask_dev = torch.ones_like(ids_dev)
+    n_samples = [wave_np.shape[1]] * B
+    tokens_host = torch.empty((B * world, ids_np.shape[1] + NEW_TOKENS), dtype=torch.int64).pin_memory()
+
+    def step(from_host: bool):
+        if from_host:
+            w = wave_host.to(dev, non_blocking=True)
+            ids = ids_host.to(dev, non_blocking=True)
+        else:
+            w, ids = wave_dev, ids_dev
+        feats = fe.from_device_waveform(w, n_samples)
+        model._mark("mel_done")
+        out = model.generate(input_ids=ids, attention_mask=mask_dev, input_features=feats["input_features"],
+                             input_features_mask=feats["input_features_mask"], max_new_tokens=NEW_TOKENS, do_sample=False)
+        out = gather_tokens(out)                      # the path's only collective (NCCL all-gather of int64 ids)
+        if from_host:
+            tokens_host.copy_(out, non_blocking=True)  # D2H read of the step's result
+        return out
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n_steps, from_host, collect_stages=False):
+        barrier()
+        ops.LAUNCHES = 0
+        stages = []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_steps):
+            if collect_stages:
+                model.stage_events = []
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                model.stage_events.append(("step_start", ev))
+            step(from_host)
+            if collect_stages:
+                stages.append(model.stage_events)
+                model.stage_events = None
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            import torch.distributed as dist
+
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, ops.LAUNCHES, stages
+
+    for _ in range(max(args.warmup, 3)):
+        step(False)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_dev, launches, stages = timed(args.steps, from_host=False, collect_stages=True)
+    clocks = sampler.stop() if rank == 0 else None
+    step(True)  # warm the host path (pinned staging, H2D)
+    ms_e2e, _, _ = timed(args.steps, from_host=True)
+
+    # one profiled step (per-kernel CUDA events around every GEMM / attention / log-mel launch)
+    ops.PROFILE = {}
+    torch.cuda.synchronize()
+    step(False)
+    torch.cuda.synchronize()
+    prof, ops.PROFILE = ops.PROFILE, None
+
+    if rank != 0:
+        return
+    peaks = measured_peaks()
+    n_tok_total = B * world * NEW_TOKENS
+    ms_step = ms_dev / args.steps
+    # stage breakdown (rank 0, mean over steps)
+    names = ["mel", "encode_project", "prefill", "decode"]
+    keys = [("step_start", "mel_done"), ("start", "audio_done"), ("audio_done", "prefill_done"), ("prefill_done", "decode_done")]
+    stage_ms = {}
+    for nm, (a, b) in zip(names, keys):
+        vals = []
+        for evs in stages:
+            d = dict(evs)
+            if a in d and b in d:
+                vals.append(d[a].elapsed_time(d[b]))
+        stage_ms[nm] = sum(vals) / len(vals) if vals else None
+    audio_ms = (stage_ms["mel"] or 0) + (stage_ms["encode_project"] or 0)
+    audio_s_per_s = B * world * CLIP_S / (audio_ms / 1e3) if audio_ms else None
+    decode_tok_s = B * world * (NEW_TOKENS - 1) / (stage_ms["decode"] / 1e3) if stage_ms["decode"] else None
+
+    # per-kernel table from the profiled step
+    table = []
+    for key, evs in prof.items():
+        kind, a, b, c, flags = key
+        ms_list = [e0.elapsed_time(e1) for e0, e1 in evs]
+        tot = sum(ms_list)
+        if kind == "gemm":
+            n_feat_w = b * 2 if (flags & 8) else b
+            flops = 2.0 * a * n_feat_w * c
+            bytes_alg = 2.0 * (a * c + n_feat_w * c + a * b)
+            table.append({"kernel": "gemm_tcgen05", "n_tok": a, "n_feat": b, "K": c, "flags": flags, "launches": len(evs), "ms_total": tot,
+                          "tflops": flops * len(evs) / (tot * 1e-3) / 1e12, "gbs": bytes_alg * len(evs) / (tot * 1e-3) / 1e9,
+                          "flops_per_launch": flops, "bytes_per_launch": bytes_alg})
+        elif kind == "attention":
+            D = flags // 2
+            causal = flags & 1
+            flops = 4.0 * a * b * c * D * (0.5 if causal else 1.0)
+            table.append({"kernel": "attention_tcgen05", "bh": a, "Tq": b, "Tk": c, "D": D, "causal": causal, "launches": len(evs),
+                          "ms_total": tot, "tflops": flops * len(evs) / (tot * 1e-3) / 1e12, "flops_per_launch": flops})
+        elif kind == "logmel":
+            bytes_alg = a * (b * 4 + 128 * (b // 160) * 4)
+            table.append({"kernel": "logmel", "n_win": a, "launches": len(evs), "ms_total": tot, "gbs": bytes_alg * len(evs) / (tot * 1e-3) / 1e9,
+                          "bytes_per_launch": bytes_alg})
+    table.sort(key=lambda r: -r["ms_total"])
+    top = next((r for r in table if r["kernel"] == "gemm_tcgen05"), None)
+    ncu = {}
+    ncu_file = ROOT / "profiles" / "ncu_summary.json"
+    if ncu_file.exists():
+        try:
+            ncu = json.loads(ncu_file.read_text())
+        except Exception:
+            ncu = {}
+    roofline = None
+    if top:
+        tensor_bound = top["n_tok"] > 64
+        if tensor_bound:
+            peak = peaks["bf16_tflops_sustained"]
+            roofline = {"kernel": f"gemm_tcgen05 n_tok={top['n_tok']} n_feat={top['n_feat']} K={top['K']} flags={top['flags']}",
+                        "bound": "tensor", "achieved": top["tflops"], "peak": peak, "unit": "TFLOP/s", "frac": top["tflops"] / peak,
+                        "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
+                        "traffic": ncu.get("gemm_prefill_traffic_bytes")}
+        else:
+            peak = peaks["hbm_gbs"]
+            roofline = {"kernel": f"gemm_tcgen05(swap) n_tok={top['n_tok']} n_feat={top['n_feat']} K={top['K']}", "bound": "hbm",
+                        "achieved": top["gbs"], "peak": peak, "unit": "GB/s", "frac": top["gbs"] / peak, "peak_source": peaks["source"],
+                        "traffic": ncu.get("gemm_decode_traffic_bytes")}
+    # decode-step HBM roofline (whole step): weights once + KV of the live context
+    dec_bytes = 2.0 * (6525618176 + 544997376) + 57344.0 * (780 + 64) * B
+    decode_roofline = None
+    if stage_ms["decode"]:
+        step_ms = stage_ms["decode"] / (NEW_TOKENS - 1)
+        gbs = dec_bytes / (step_ms * 1e-3) / 1e9
+        decode_roofline = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                           "ms_per_decode_step": step_ms, "bytes_per_step": dec_bytes}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            cpu = cpu_reference(sample="small")
+        except Exception as e:  # the baseline is reported context; never let it kill the GPU line
+            cpu = {"error": repr(e)}
+
+    line = {
+        "metric": METRIC, "value": n_tok_total / (ms_step / 1e3), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic (seeded noise audio, random-init AF3-7B weights, random prompt ids)",
+        "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world, "clip_seconds": CLIP_S, "prompt_len": int(ids_np.shape[1]),
+                   "new_tokens": NEW_TOKENS, "parallelism": f"dp{world} (batch sharded, weights replicated)",
+                   "l2": "inputs larger than L2 (16.5 GB of weights streamed every step; no flush needed)"},
+        "e2e": {"value": n_tok_total / (ms_e2e / args.steps / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": int(wave_host.numel() * 4 + ids_host.numel() * 8),
+                "d2h_bytes_per_step": int(tokens_host.numel() * 8), "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+        "audio_s_per_s": audio_s_per_s, "decode_tok_s": decode_tok_s, "stage_ms": stage_ms,
+        "roofline": roofline, "roofline_decode_step": decode_roofline, "kernels": table[:12],
+        "cpu_baseline": cpu, "clocks": clocks,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------- reference (CPU)
+class CpuReference:
+    """The reference's own PyTorch path (unmodified HF classes) on this box's host cores, bf16, all threads.
+    Bounded samples of the SAME workload, composed linearly where the path is linear:
+      * audio: WhisperFeatureExtractor + full 32-layer AF-Whisper encoder + projector on n_win windows of 30 s
+      * prefill: Qwen2 decoder on one 780-token prompt with `layers` of the 28 identical layers (x 28/layers) + LM head
+      * decode: cached q_len=1 steps at the workload's batch 32 / context 780 on the same sampled layers
+    """
+
+    def __init__(self, layers: int = 2, n_win: int = 1, n_dec: int = 1):
+        from oracle import af3_oracle as O  # the checker; allowed here (cpu_baseline / --impl reference legs only)
+        from transformers import AudioFlamingo3Config, AudioFlamingo3ForConditionalGeneration
+
+        self.O = O
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+        self.layers, self.n_win, self.n_dec, self.S = layers, n_win, n_dec, 780
+        text = dict(O.AF3_7B["text"])
+        theta = text.pop("rope_theta")
+        text["num_hidden_layers"] = layers
+        self.cfg = AudioFlamingo3Config(audio_config=dict(O.AF3_7B["audio"]),
+                                        text_config=dict(text, rope_parameters={"rope_type": "default", "rope_theta": theta}),
+                                        audio_token_id=151669)
+        with torch.device("meta"):
+            model = AudioFlamingo3ForConditionalGeneration(self.cfg)
+        model = model.to_empty(device="cpu").to(torch.bfloat16).eval()
+        torch.manual_seed(0)
+        base = (torch.randn(1 << 22) * 0.02).to(torch.bfloat16)  # N(0, 0.02) block tiled into every tensor (fast init)
+        with torch.no_grad():
+            for name, p in model.named_parameters():
+                flat = p.view(-1)
+                if name.endswith("bias"):
+                    flat.zero_()
+                elif "norm" in name:
+                    flat.fill_(1.0)
+                else:
+                    for o in range(0, flat.numel(), base.numel()):
+                        n = min(base.numel(), flat.numel() - o)
+                        flat[o:o + n] = base[:n]
+        for m in model.modules():  # rotary inv_freq is a non-persistent buffer: recompute after to_empty
+            if hasattr(m, "inv_freq") and hasattr(m, "compute_default_rope_parameters"):
+                inv, _ = m.compute_default_rope_parameters(m.config)
+                m.inv_freq = inv
+                m.original_inv_freq = inv.clone()
+        self.model = model
+
+    @torch.no_grad()
+    def sample(self):
+        from transformers.cache_utils import DynamicCache
+
+        O, cfg, model, S, layers, n_win, n_dec = self.O, self.cfg, self.model, self.S, self.layers, self.n_win, self.n_dec
+        t_all0 = time.time()
+        waves = O.synth_waveforms(n_win, CLIP_S, seed=1)
+        t0 = time.time()
+        feats, fmask = O.hf_features(waves)
+        t_mel = time.time() - t0
+        t0 = time.time()
+        model.get_audio_features(feats.to(torch.bfloat16), fmask)
+        t_enc = time.time() - t0
+        lm = model.language_model
+        emb = torch.randn(1, S, cfg.text_config.hidden_size).to(torch.bfloat16) * 0.02
+        t0 = time.time()
+        lm(inputs_embeds=emb, use_cache=True, logits_to_keep=1)
+        t_pre_layers = time.time() - t0
+        # decode at the workload's batch/context with a synthetic cache (prefilling 32 x 780 on the CPU would take minutes)
+        Bd = B_PER_GPU
+        cache = DynamicCache(config=cfg.text_config)
+        Hkv, D = cfg.text_config.num_key_value_heads, cfg.text_config.hidden_size // cfg.text_config.num_attention_heads
+        for li in range(layers):
+            cache.update(torch.randn(Bd, Hkv, S, D).to(torch.bfloat16), torch.randn(Bd, Hkv, S, D).to(torch.bfloat16), li)
+        ids = torch.randint(0, 1000, (Bd, 1))
+        t0 = time.time()
+        for i in range(n_dec):
+            lm(input_ids=ids, attention_mask=torch.ones(Bd, S + 1 + i, dtype=torch.long), past_key_values=cache, use_cache=True, logits_to_keep=1)
+        t_dec_layers = (time.time() - t0) / n_dec
+        x1 = torch.randn(Bd, cfg.text_config.hidden_size).to(torch.bfloat16)
+        t0 = time.time()
+        lm.lm_head(x1)
+        t_head = time.time() - t0
+        scale = 28.0 / layers
+        B = B_PER_GPU
+        t_audio = (t_mel + t_enc) / n_win * B
+        t_prefill = max(t_pre_layers - t_head, 0.0) * scale * B + t_head
+        t_decode_step = max(t_dec_layers - t_head, 0.0) * scale + t_head
+        total = t_audio + t_prefill + (NEW_TOKENS - 1) * t_decode_step
+        import transformers
+
+        return {
+            "value": B * NEW_TOKENS / total, "unit": "tokens/s", "cores": self.cores, "kind": "reference",
+            "sample": (f"HF transformers {transformers.__version__} bf16 on CPU, {self.cores} threads: mel+32-layer encoder+projector on {n_win} x 30 s "
+                       f"window(s) (x{B}/{n_win}); prefill of one 780-token prompt on {layers}/28 decoder layers (x28/{layers} x{B}); "
+                       f"{n_dec} cached decode step(s) at batch 32 / context 780 on {layers}/28 layers (x28/{layers}) x127; LM head timed once"),
+            "audio_s_per_s": B * CLIP_S / t_audio, "decode_tok_s": B / t_decode_step,
+            "seconds": {"mel_per_window": t_mel / n_win, "encode_per_window": t_enc / n_win, "prefill_sampled_layers_1seq": t_pre_layers,
+                        "decode_step_sampled_layers_b32": t_dec_layers, "lm_head_b32": t_head, "sample_wall": time.time() - t_all0},
+            "estimated_workload_seconds": total,
+        }
+
+
+def cpu_reference(sample: str = "small"):
+    return CpuReference(layers=2, n_win=1, n_dec=1).sample()
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    ref = CpuReference(layers=2, n_win=1, n_dec=2)
+    t0 = time.time()
+    for _ in range(max(args.warmup, 0)):
+        ref.sample()
+        if time.time() - t0 > 60:
+            break
+    vals = []
+    t0 = time.time()
+    for _ in range(max(args.steps, 1)):
+        vals.append(ref.sample())
+        if time.time() - t0 > 150:  # keep the whole run within a few minutes on small hosts
+            break
+    total = sum(r["estimated_workload_seconds"] for r in vals) / len(vals)
+    v = B_PER_GPU * NEW_TOKENS / total
+    res = dict(vals[-1], value=v)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "tokens/s", "n_gpus": world, "steps": len(vals), "warmup": args.warmup,
+        "ms_per_step": total * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic (seeded noise audio, random-init AF3-7B weights)",
+        "config": {"workload": WORKLOAD, "per_gpu_batch": B_PER_GPU, "global_batch": B_PER_GPU, "clip_seconds": CLIP_S, "prompt_len": 780,
+                   "new_tokens": NEW_TOKENS, "parallelism": "host CPU, all threads"},
+        "cpu_baseline": res,
+        "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: the AF3 hot path has no CPU fallback"}))
+        sys.exit(1)
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
