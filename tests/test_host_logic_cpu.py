@@ -1,0 +1,99 @@
+"""Host-side logic of the path (no GPU): sharding arithmetic, the token gather over world_size-2 gloo, prompt
+helpers, module surface / state_dict key parity with the reference."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+from hypothesis import given, settings, strategies as st
+
+from audio_flamingo_b200.processing import expand_audio_tokens, left_pad, split_windows
+from audio_flamingo_b200.sharding import gather_tokens, shard_rows
+
+
+@given(st.integers(0, 300), st.integers(1, 8))
+@settings(max_examples=200, deadline=None)
+def test_shard_rows_partitions(n, world):
+    spans = [shard_rows(n, world, r) for r in range(world)]
+    assert spans[0][0] == 0 and spans[-1][1] == n
+    assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+    sizes = [b - a for a, b in spans]
+    assert max(sizes) - min(sizes) <= 1
+
+
+@given(st.lists(st.integers(1, 20), min_size=1, max_size=40), st.integers(1, 8))
+@settings(max_examples=200, deadline=None)
+def test_shard_rows_weighted(weights, world):
+    n = len(weights)
+    spans = [shard_rows(n, world, r, weights) for r in range(world)]
+    assert spans[0][0] == 0 and spans[-1][1] == n
+    assert all(0 <= a <= b <= n for a, b in spans)
+    assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+    loads = [sum(weights[a:b]) for a, b in spans]
+    assert max(loads) <= sum(weights) / world + max(weights)  # balanced up to one sequence
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gather_worker(rank, world, port, counts):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    L = 7
+    local = torch.arange(counts[rank] * L, dtype=torch.int64).view(counts[rank], L) + 1000 * rank
+    out = gather_tokens(local, counts)
+    exp = torch.cat([torch.arange(c * L, dtype=torch.int64).view(c, L) + 1000 * r for r, c in enumerate(counts)])
+    assert torch.equal(out, exp), (rank, out, exp)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("counts", [[4, 4], [3, 1]])
+def test_gather_tokens_gloo_world2(counts):
+    import torch.multiprocessing as mp
+
+    mp.spawn(_gather_worker, args=(2, _free_port(), counts), nprocs=2, join=True)
+
+
+def test_gather_identity_without_process_group():
+    t = torch.arange(6).view(2, 3)
+    assert gather_tokens(t) is t
+
+
+def test_prompt_helpers():
+    ids = expand_audio_tokens([5, 9, 7], 9, 4)
+    assert ids == [5, 9, 9, 9, 9, 7]
+    a, m = left_pad([[1, 2, 3], [4]], pad_id=0)
+    assert a.tolist() == [[1, 2, 3], [0, 0, 4]] and m.tolist() == [[1, 1, 1], [0, 0, 1]]
+    chunks, per = split_windows([np.zeros(480000 * 25, np.float32)])
+    assert per == [20] and len(chunks) == 20  # 600 s cap (AF3P:82,160)
+
+
+def test_state_dict_keys_match_reference():
+    """Same module tree / parameter names / shapes as the reference model (drop-in load_state_dict)."""
+    from oracle import af3_oracle as O
+
+    from audio_flamingo_b200 import AudioFlamingo3ForConditionalGeneration
+
+    ref = O.hf_model("tiny", seed=0)
+    ours = AudioFlamingo3ForConditionalGeneration(ref.config)
+    a = {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+    b = {k: tuple(v.shape) for k, v in ours.state_dict().items()}
+    assert a == b
+
+
+def test_model_refuses_cpu():
+    from oracle import af3_oracle as O
+
+    from audio_flamingo_b200 import AF3Error, AudioFlamingo3Encoder
+
+    enc = AudioFlamingo3Encoder(O.hf_config("tiny").audio_config)
+    with pytest.raises(AF3Error, match="no CPU fallback"):
+        enc(torch.zeros(1, 128, 3000), torch.ones(1, 3000, dtype=torch.int32))
