@@ -15,7 +15,7 @@ def __getattr__(name):  # lazy: keep `import audio_flamingo_b200` light (torch/t
         from . import modeling
 
         return getattr(modeling, name)
-    if name in ("AF3FeatureExtractor", "split_windows", "tokens_per_sample", "expand_audio_tokens", "left_pad",
+    if name in ("AF3FeatureExtractor", "split_windows", "tokens_per_sample", "expand_audio_tokens", "expand_audio_spans", "left_pad",
                 "audio_token_length"):
         from . import processing
 

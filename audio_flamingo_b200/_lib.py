@@ -19,6 +19,8 @@ SIGNATURES = {
     "af3_last_error": (C.c_char_p, []),
     "af3_abi_version": (_i, []),
     "af3_gemm_bf16": (_i, [_p, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _p, _p, _i, _i]),
+    "af3_gemm_workspace_bytes": (_sz, []),
+    "af3_gemm_bf16_ws": (_i, [_p, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p, _sz]),
     "af3_pack_gate_up": (_i, [_p, _p, _p, _p, _i, _i]),
     "af3_logmel": (_i, [_p, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
     "af3_im2col_conv1": (_i, [_p, _p, _i, _p, _i, _i, _i]),
@@ -29,7 +31,7 @@ SIGNATURES = {
     "af3_attention": (_i, [_p, _p, _i, _p, _p, _i, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _f, _i, _p, _p]),
     "af3_rope_kv_append": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "af3_decode_attention": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _f]),
-    "af3_decode_attention_scratch_bytes": (_sz, [_i, _i, _i]),
+    "af3_decode_attention_scratch_bytes": (_sz, [_i, _i, _i, _i]),
     "af3_embed_scatter": (_i, [_p, _p, _i, _p, _i, _i64, _p, _i, _i, _p, _p, _p, _p]),
     "af3_argmax": (_i, [_p, _p, _i, _i, _p]),
 }

@@ -6,7 +6,9 @@
 namespace af3 {
 const char* last_error_cstr();
 int gemm_bf16(cudaStream_t stream, const bf16* x, int ldx, const bf16* w, int ldw, void* out, int ldo, int n_tok,
-              int n_feat, int K, int flags, const bf16* bias, const bf16* resid, int ld_res, int res_period);
+              int n_feat, int K, int flags, const bf16* bias, const bf16* resid, int ld_res, int res_period,
+              void* workspace, size_t workspace_bytes);
+size_t gemm_workspace_bytes();
 int logmel(cudaStream_t stream, const float* wave, int n_win, int n_samples, const float* hann, const float* table,
            const float* filt, const int* klo, const int* khi, float* out, int* win_max);
 int layernorm(cudaStream_t, const bf16*, bf16*, const bf16*, const bf16*, int, int, float);
@@ -23,7 +25,7 @@ int argmax(cudaStream_t, const float*, int, int, int64_t*);
 int attention(cudaStream_t stream, const bf16* q, int ldq, const bf16* k, const bf16* v, int ldk, int kv_layout,
               int Tk_pitch, bf16* out, int ldo, int B, int H, int Hkv, int D, int Tq, int Tk, float scale, int causal,
               const int* kv_len, const int* kv_start);
-size_t decode_attention_scratch_bytes(int B, int H, int D);
+size_t decode_attention_scratch_bytes(int B, int H, int D, int Tmax);
 int decode_attention(cudaStream_t stream, const bf16* qkv, const bf16* k_cache, const bf16* v_cache, bf16* out,
                      float* scratch, int B, int H, int Hkv, int D, int Tmax, const int* ctx_len, const int* kv_start,
                      float scale);
@@ -42,7 +44,16 @@ int af3_abi_version(void) { return 1; }
 int af3_gemm_bf16(void* stream, const void* x, int ldx, const void* w, int ldw, void* out, int ldo, int n_tok, int n_feat,
                   int K, int flags, const void* bias, const void* resid, int ld_res, int res_period) {
     return af3::gemm_bf16(S(stream), B16(x), ldx, B16(w), ldw, out, ldo, n_tok, n_feat, K, flags, B16(bias), B16(resid),
-                          ld_res, res_period);
+                          ld_res, res_period, nullptr, 0);
+}
+
+size_t af3_gemm_workspace_bytes(void) { return af3::gemm_workspace_bytes(); }
+
+int af3_gemm_bf16_ws(void* stream, const void* x, int ldx, const void* w, int ldw, void* out, int ldo, int n_tok,
+                     int n_feat, int K, int flags, const void* bias, const void* resid, int ld_res, int res_period,
+                     void* workspace, size_t workspace_bytes) {
+    return af3::gemm_bf16(S(stream), B16(x), ldx, B16(w), ldw, out, ldo, n_tok, n_feat, K, flags, B16(bias), B16(resid),
+                          ld_res, res_period, workspace, workspace_bytes);
 }
 
 int af3_pack_gate_up(void* stream, const void* gate, const void* up, void* packed, int F, int K) {
@@ -87,7 +98,9 @@ int af3_rope_kv_append(void* stream, void* qkv, void* k_cache, void* v_cache, in
                                kv_start, inv_freq);
 }
 
-size_t af3_decode_attention_scratch_bytes(int B, int H, int D) { return af3::decode_attention_scratch_bytes(B, H, D); }
+size_t af3_decode_attention_scratch_bytes(int B, int H, int D, int Tmax) {
+    return af3::decode_attention_scratch_bytes(B, H, D, Tmax);
+}
 int af3_decode_attention(void* stream, const void* qkv, const void* k_cache, const void* v_cache, void* out,
                          float* scratch, int B, int H, int Hkv, int D, int Tmax, const int* ctx_len,
                          const int* kv_start, float scale) {

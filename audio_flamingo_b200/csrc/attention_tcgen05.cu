@@ -20,6 +20,13 @@ constexpr int AT_BN = 128;   // keys per tile
 constexpr int AT_NSTG = 3;   // K/V ring slots
 constexpr float LOG2E = 1.4426950408889634f;
 
+// 2^x on the SFU (ex2.approx.ftz): relative error ~2^-22, far below the bf16 rounding applied to P
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 struct AttnArgs {
     int Tq, Tk, H, Hkv, causal, kv_layout;
     float scale_log2;  // softmax scale * log2(e)
@@ -194,25 +201,44 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             mbar_wait(s_full, t & 1);
             tc_fence_after();
             const bool need_mask = (k0 < kvs) || (k0 + AT_BN > kvl) || (a.causal && k0 + AT_BN - 1 > q0 + (a.Tk - a.Tq));
-            // ---- pass 1: row max
+            // keys visible to this row inside the tile: local index in [vlo, vhi]  (one unsigned compare per element)
+            const int vlo = max(kvs - k0, 0);
+            const int vhi = min(min(kvl - 1, causal_hi) - k0, AT_BN - 1);
+            const uint32_t vspan = static_cast<uint32_t>(vhi - vlo);  // wraps to huge when the row sees no key: handled below
+            const bool row_empty = vhi < vlo;
+            // ---- pass 1: row max (two 32-column TMEM loads in flight)
             float m_tile = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < AT_BN / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld32(tmem_S + lane_off + c * 32, v);
+#pragma unroll
+            for (int c = 0; c < AT_BN / 64; ++c) {
+                uint32_t v0[32], v1[32];
+                tmem_ld32(tmem_S + lane_off + c * 64, v0);
+                tmem_ld32(tmem_S + lane_off + c * 64 + 32, v1);
                 tmem_ld_wait();
+                float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
                 if (need_mask) {
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        const int key = k0 + c * 32 + e;
-                        const bool ok = key >= kvs && key < kvl && key <= causal_hi;
-                        m_tile = fmaxf(m_tile, ok ? __uint_as_float(v[e]) : -INFINITY);
+                    for (int e = 0; e < 32; e += 2) {
+                        const bool ok0 = static_cast<uint32_t>(c * 64 + e - vlo) <= vspan;
+                        const bool ok1 = static_cast<uint32_t>(c * 64 + e + 1 - vlo) <= vspan;
+                        const bool ok2 = static_cast<uint32_t>(c * 64 + 32 + e - vlo) <= vspan;
+                        const bool ok3 = static_cast<uint32_t>(c * 64 + 33 + e - vlo) <= vspan;
+                        mx0 = fmaxf(mx0, ok0 ? __uint_as_float(v0[e]) : -INFINITY);
+                        mx1 = fmaxf(mx1, ok1 ? __uint_as_float(v0[e + 1]) : -INFINITY);
+                        mx2 = fmaxf(mx2, ok2 ? __uint_as_float(v1[e]) : -INFINITY);
+                        mx3 = fmaxf(mx3, ok3 ? __uint_as_float(v1[e + 1]) : -INFINITY);
                     }
                 } else {
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) m_tile = fmaxf(m_tile, __uint_as_float(v[e]));
+                    for (int e = 0; e < 32; e += 2) {
+                        mx0 = fmaxf(mx0, __uint_as_float(v0[e]));
+                        mx1 = fmaxf(mx1, __uint_as_float(v0[e + 1]));
+                        mx2 = fmaxf(mx2, __uint_as_float(v1[e]));
+                        mx3 = fmaxf(mx3, __uint_as_float(v1[e + 1]));
+                    }
                 }
+                m_tile = fmaxf(m_tile, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
             }
+            if (need_mask && row_empty) m_tile = -INFINITY;
             m_tile *= sl2;  // sl2 > 0: max commutes with the scale
             const float m_new = fmaxf(m_ref, m_tile);
             // ---- wait until P.V of the previous tile retired: P buffer and O are ours again
@@ -240,32 +266,44 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             } else {
                 m_ref = m_new;
             }
-            const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
-            // ---- pass 2: probabilities -> bf16 P in the K-major 128B-swizzled layout, row sums in fp32
-            float l_tile = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < AT_BN / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld32(tmem_S + lane_off + c * 32, v);
+            const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
+            // ---- pass 2: p = 2^(s*scale - m) -> bf16 P in the K-major 128B-swizzled layout, row sums in fp32
+            float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+#pragma unroll
+            for (int c = 0; c < AT_BN / 64; ++c) {
+                uint32_t v0[32], v1[32];
+                tmem_ld32(tmem_S + lane_off + c * 64, v0);
+                tmem_ld32(tmem_S + lane_off + c * 64 + 32, v1);
                 tmem_ld_wait();
-                float p[32];
+                uint8_t* prow = sP + c * 16384 + row * 128;  // keys c*64 .. c*64+63 = swizzle block c
 #pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    const int key = k0 + c * 32 + e;
-                    const bool ok = !need_mask || (key >= kvs && key < kvl && key <= causal_hi);
-                    p[e] = ok ? exp2f(__uint_as_float(v[e]) * sl2 - m_use) : 0.f;
-                    l_tile += p[e];
-                }
-                // keys c*32 .. c*32+31 of this row: block kb = c/2, 16-byte chunks (c&1)*4 .. +3
-                uint8_t* prow = sP + (c >> 1) * 16384 + row * 128;
+                for (int hh = 0; hh < 2; ++hh) {
+                    uint32_t(&v)[32] = hh ? v1 : v0;
+                    uint32_t pk[16];
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const int chunk = (c & 1) * 4 + g;
-                    const uint4 pk = make_uint4(pack_bf16x2(p[8 * g], p[8 * g + 1]), pack_bf16x2(p[8 * g + 2], p[8 * g + 3]),
-                                                pack_bf16x2(p[8 * g + 4], p[8 * g + 5]), pack_bf16x2(p[8 * g + 6], p[8 * g + 7]));
-                    *reinterpret_cast<uint4*>(prow + ((chunk ^ (row & 7)) << 4)) = pk;
+                    for (int e = 0; e < 32; e += 2) {
+                        float p0 = fast_exp2(fmaf(__uint_as_float(v[e]), sl2, neg_m));
+                        float p1 = fast_exp2(fmaf(__uint_as_float(v[e + 1]), sl2, neg_m));
+                        if (need_mask) {
+                            p0 = (static_cast<uint32_t>(c * 64 + hh * 32 + e - vlo) <= vspan && !row_empty) ? p0 : 0.f;
+                            p1 = (static_cast<uint32_t>(c * 64 + hh * 32 + e + 1 - vlo) <= vspan && !row_empty) ? p1 : 0.f;
+                        }
+                        if (e & 2) {
+                            l2 += p0;
+                            l3 += p1;
+                        } else {
+                            l0 += p0;
+                            l1 += p1;
+                        }
+                        pk[e >> 1] = pack_bf16x2(p0, p1);
+                    }
+#pragma unroll
+                    for (int g = 0; g < 4; ++g)
+                        *reinterpret_cast<uint4*>(prow + (((hh * 4 + g) ^ (row & 7)) << 4)) =
+                            make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
                 }
             }
+            const float l_tile = (l0 + l1) + (l2 + l3);
             l_run = l_run * alpha + l_tile;
             fence_proxy_async_smem();
             tc_fence_before();

@@ -262,57 +262,65 @@ int pack_gate_up(cudaStream_t stream, const bf16* gate, const bf16* up, bf16* pa
 
 // ---------------------------------------------------------------------------------------------------------
 // Rotary embedding + KV append ([O] Q2M:100-146 rotate-half RoPE with fp32 tables cast to bf16; CACHE:119-120).
-// One thread = one (token, head, i < D/2) pair (i, i + D/2).  Every bf16 op of the reference rounds: q*cos,
-// rotate_half(q)*sin and their sum are each rounded to bf16.
+// Every bf16 op of the reference rounds: q*cos, rotate_half(q)*sin and their sum are each rounded to bf16.
+// One thread = one (token, 8-wide d chunk of the first half): cos/sin are computed once and reused for every head;
+// all accesses are 16-byte vectors (chunk d..d+7 and its rotate-half partner d+D/2..d+D/2+7).
 __global__ void __launch_bounds__(256)
 rope_kv_append_kernel(bf16* __restrict__ qkv, bf16* __restrict__ k_cache, bf16* __restrict__ v_cache, int B, int T,
                       int H, int Hkv, int D, int Tmax, int pos0, const int* __restrict__ pos0_dev,
                       const int* __restrict__ kv_start, const float* __restrict__ inv_freq) {
     const int half = D >> 1;
+    const int cpt = half >> 3;  // 8-wide chunks per token half
     const int heads = H + 2 * Hkv;
-    const long long total = static_cast<long long>(B) * T * heads * half;
+    const long long total = static_cast<long long>(B) * T * cpt;
     const int p0 = pos0_dev ? *pos0_dev : pos0;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int d = static_cast<int>(i % half);
-        long long r = i / half;
-        const int h = static_cast<int>(r % heads);
-        r /= heads;
-        const int t = static_cast<int>(r % T);
-        const int b = static_cast<int>(r / T);
-        bf16* row = qkv + (static_cast<size_t>(b) * T + t) * heads * D + static_cast<size_t>(h) * D;
+        const int ch = static_cast<int>(i % cpt);
+        const long long bt = i / cpt;
+        const int t = static_cast<int>(bt % T);
+        const int b = static_cast<int>(bt / T);
+        const int d0 = ch * 8;
         const int cpos = p0 + t;  // cache slot
-        if (h >= H + Hkv) {       // value head: plain copy into the cache
-            const int hk = h - H - Hkv;
-            bf16* dst = v_cache + ((static_cast<size_t>(b) * Hkv + hk) * Tmax + cpos) * D;
-            dst[d] = row[d];
-            dst[d + half] = row[d + half];
-            continue;
-        }
         int pos = cpos - (kv_start ? kv_start[b] : 0);
         if (pos < 0) pos = 1;  // padded slot: position_ids.masked_fill_(mask == 0, 1) (GEN:721)
-        const float fr = inv_freq[d] * static_cast<float>(pos);
-        const float c = bf16_round(cosf(fr)), s = bf16_round(sinf(fr));
-        const float x1 = __bfloat162float(row[d]), x2 = __bfloat162float(row[d + half]);
-        const float o1 = bf16_round(bf16_round(x1 * c) + bf16_round(-x2 * s));
-        const float o2 = bf16_round(bf16_round(x2 * c) + bf16_round(x1 * s));
-        if (h < H) {
-            row[d] = __float2bfloat16_rn(o1);
-            row[d + half] = __float2bfloat16_rn(o2);
-        } else {
-            const int hk = h - H;
-            bf16* dst = k_cache + ((static_cast<size_t>(b) * Hkv + hk) * Tmax + cpos) * D;
-            dst[d] = __float2bfloat16_rn(o1);
-            dst[d + half] = __float2bfloat16_rn(o2);
+        float c[8], sn[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float fr = inv_freq[d0 + e] * static_cast<float>(pos);
+            c[e] = bf16_round(cosf(fr));
+            sn[e] = bf16_round(sinf(fr));
+        }
+        bf16* tok = qkv + static_cast<size_t>(bt) * heads * D;
+        for (int h = 0; h < H + Hkv; ++h) {
+            bf16* row = tok + static_cast<size_t>(h) * D;
+            float x1[8], x2[8], o1[8], o2[8];
+            unpack8(*reinterpret_cast<const uint4*>(row + d0), x1);
+            unpack8(*reinterpret_cast<const uint4*>(row + d0 + half), x2);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                o1[e] = bf16_round(bf16_round(x1[e] * c[e]) + bf16_round(-x2[e] * sn[e]));
+                o2[e] = bf16_round(bf16_round(x2[e] * c[e]) + bf16_round(x1[e] * sn[e]));
+            }
+            bf16* dst = row;
+            if (h >= H) dst = k_cache + ((static_cast<size_t>(b) * Hkv + (h - H)) * Tmax + cpos) * D;
+            *reinterpret_cast<uint4*>(dst + d0) = pack8(o1);
+            *reinterpret_cast<uint4*>(dst + d0 + half) = pack8(o2);
+        }
+        for (int hk = 0; hk < Hkv; ++hk) {  // value heads: plain copy into the cache
+            const bf16* row = tok + static_cast<size_t>(H + Hkv + hk) * D;
+            bf16* dst = v_cache + ((static_cast<size_t>(b) * Hkv + hk) * Tmax + cpos) * D;
+            *reinterpret_cast<uint4*>(dst + d0) = *reinterpret_cast<const uint4*>(row + d0);
+            *reinterpret_cast<uint4*>(dst + d0 + half) = *reinterpret_cast<const uint4*>(row + d0 + half);
         }
     }
 }
 
 int rope_kv_append(cudaStream_t stream, bf16* qkv, bf16* k_cache, bf16* v_cache, int B, int T, int H, int Hkv, int D,
                    int Tmax, int pos0, const int* pos0_dev, const int* kv_start, const float* inv_freq) {
-    AF3_REQUIRE(D % 2 == 0 && inv_freq, "rope: bad head dim / missing inv_freq");
+    AF3_REQUIRE(D % 16 == 0 && inv_freq, "rope: head dim must be a multiple of 16 / missing inv_freq");
     AF3_REQUIRE(pos0_dev || pos0 + T <= Tmax, "rope: KV cache overflow");
-    const long long total = static_cast<long long>(B) * T * (H + 2 * Hkv) * (D / 2);
+    const long long total = static_cast<long long>(B) * T * (D / 16);
     if (total <= 0) return 0;
     const int grid = static_cast<int>(((total + 255) / 256) < 148ll * 32 ? ((total + 255) / 256) : 148ll * 32);
     rope_kv_append_kernel<<<grid, 256, 0, stream>>>(qkv, k_cache, v_cache, B, T, H, Hkv, D, Tmax, pos0, pos0_dev, kv_start,

@@ -34,18 +34,27 @@ struct GemmArgs {
     int ld_res;
     int res_period;  // residual row = tok % res_period (positional-embedding add); 0 = plain
     int flags;
+    // split-K (swap mode only): each output tile is computed by k_splits CTAs over disjoint K ranges; partial fp32
+    // tiles go to `ws`, the CTA that arrives last (per-tile counter) sums them in split order (deterministic) and
+    // runs the fused epilogue.  Fills the 148 SMs when the weight matrix has only 28-36 row tiles (decode step).
+    int tma_epi;    // normal mode: stage the output tile in smem and write it with TMA (coalesced); residual via TMA too
+    int k_splits;
+    float* ws;      // [tiles][k_splits][BN][128] fp32
+    int* counters;  // [tiles], zero on entry, reset to zero by the reducing CTA
 };
 
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle atom row
 
-template <int BN, int NA, int STAGES>
+template <int BN, int NA, int STAGES, bool SWAP>
 struct GemmCfg {
     static constexpr int R_BYTES = 128 * NA * BK * 2;
     static constexpr int C_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = R_BYTES + C_BYTES;
     static constexpr int ACC_COLS = NA * BN;
     static constexpr int TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128) ? 128 : (2 * ACC_COLS <= 256) ? 256 : 512;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    // normal mode: 4 epilogue warps x 2 buffers x (32 rows x 128 B) staging for the TMA-store epilogue
+    static constexpr int EPI_STAGE_BYTES = SWAP ? 0 : 4 * 2 * 4096;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
     static_assert(2 * ACC_COLS <= 512, "TMEM budget");
     static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
 };
@@ -75,17 +84,22 @@ __device__ __forceinline__ float epi_swiglu(float g, float u) {
     return bf16_round(s * u);
 }
 
-template <int BN, int NA, int STAGES, bool SWAP>
+// EPI >= 0: epilogue flags fixed at compile time (no per-element branches, full ILP across the 32-column chunk);
+// EPI < 0: generic instantiation reading a.flags at run time (odd layouts / unusual flag mixes).
+template <int BN, int NA, int STAGES, bool SWAP, int EPI>
 __global__ void __launch_bounds__(192, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_c, const GemmArgs a) {
-    using Cfg = GemmCfg<BN, NA, STAGES>;
+gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_c,
+            const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res, const GemmArgs a) {
+    using Cfg = GemmCfg<BN, NA, STAGES, SWAP>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint8_t* epi_stage = smem + STAGES * Cfg::STAGE_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(epi_stage + Cfg::EPI_STAGE_BYTES);
     uint64_t* empty = full + STAGES;
     uint64_t* tfull = empty + STAGES;
     uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* rbar = tempty + 2;  // [4 warps][2 buffers] residual-tile arrival
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + 8);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -101,6 +115,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
             mbar_init(&tfull[i], 1);
             mbar_init(&tempty[i], 128);
         }
+        for (int i = 0; i < 8; ++i) mbar_init(&rbar[i], 1);
+        if (a.tma_epi) {
+            tma_prefetch_desc(&map_out);
+            if ((((EPI >= 0) ? EPI : a.flags) & EPI_RESID) && a.res_period == 0) tma_prefetch_desc(&map_res);
+        }
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -112,8 +131,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int num_tiles = a.num_r_tiles * a.num_c_tiles;
-    const int k_blocks = (a.K + BK - 1) / BK;
+    const int k_splits = SWAP ? a.k_splits : 1;
+    const int num_tiles = a.num_r_tiles * a.num_c_tiles * k_splits;  // work items: (tile, split), split fastest
+    const int k_blocks_total = (a.K + BK - 1) / BK;
+    // K range of split s: blocks [kb_lo(s), kb_lo(s+1)), sizes differ by at most one
+    auto kb_lo = [&](int s) { return (s * k_blocks_total) / k_splits; };
 
     if (warp == 0) {
         if (lane == 0) {
@@ -121,8 +143,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
             uint32_t phase = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
                 int r, c;
-                tile_coords(t, a, r, c);
-                for (int kb = 0; kb < k_blocks; ++kb) {
+                tile_coords(t / k_splits, a, r, c);
+                const int sp = t % k_splits;
+                for (int kb = kb_lo(sp); kb < kb_lo(sp + 1); ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t* sR = smem + stage * Cfg::STAGE_BYTES;
                     uint8_t* sC = sR + Cfg::R_BYTES;
@@ -150,7 +173,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_COLS;
-                for (int kb = 0; kb < k_blocks; ++kb) {
+                const int sp = t % k_splits;
+                const int kb0 = kb_lo(sp), kb1 = kb_lo(sp + 1);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint32_t sR = smem_u32(smem + stage * Cfg::STAGE_BYTES);
@@ -161,7 +186,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
 #pragma unroll
                         for (int na = 0; na < NA; ++na) {
                             const uint64_t adesc = make_smem_desc_sw128(sR + na * 128 * BK * 2 + k * 32, 0, 1024);
-                            umma_bf16_ss(d_tmem + na * BN, adesc, bdesc, idesc, (kb | k) != 0);
+                            umma_bf16_ss(d_tmem + na * BN, adesc, bdesc, idesc, (kb > kb0) || (k != 0));
                         }
                     }
                     umma_commit(&empty[stage]);
@@ -181,12 +206,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
     } else {
         const int q = warp & 3;  // TMEM lane quarter this warp may access
         const int row_in_tile = q * 32 + lane;
-        const int flags = a.flags;
+        const int flags = (EPI >= 0) ? EPI : a.flags;
         int acc = 0;
         uint32_t acc_phase = 0;
+        uint32_t egrp = 0;             // running 64-column group counter of this warp (selects the staging buffer)
+        uint32_t rpar0 = 0, rpar1 = 0;  // residual-barrier parities per buffer
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
             int r, c;
-            tile_coords(t, a, r, c);
+            tile_coords(t / k_splits, a, r, c);
+            [[maybe_unused]] const bool swiglu = flags & EPI_SWIGLU;
+            [[maybe_unused]] const bool tma_res = a.tma_epi && (flags & EPI_RESID) && a.res_period == 0;
+            [[maybe_unused]] const int out_col_base = c * (swiglu ? BN / 2 : BN);
+            [[maybe_unused]] const int row0 = r * 128 + q * 32;
+            if constexpr (!SWAP) {
+                if (tma_res && lane == 0) {  // prefetch the residual slab of group 0 while the accumulator is still in flight
+                    bulk_wait_read<0>();
+                    const int b0 = egrp & 1;
+                    mbar_arrive_expect_tx(&rbar[q * 2 + b0], 4096);
+                    tma_load_2d(epi_stage + (q * 2 + b0) * 4096, &map_res, &rbar[q * 2 + b0], out_col_base, row0);
+                }
+            }
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * Cfg::ACC_COLS;
@@ -195,7 +234,102 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
                 const int tok = r * 128 + row_in_tile;
                 const bool row_ok = tok < a.n_tok;
                 const int res_row = (a.res_period > 0) ? (tok % a.res_period) : tok;
-                if (flags & EPI_SWIGLU) {
+                if (a.tma_epi) {
+                    // ---- smem-staged epilogue: per warp, 64 output columns at a time -> [32 rows x 128 B] swizzled slab -> TMA store
+                    const int n_groups = (swiglu ? BN / 2 : BN) / 64;
+#pragma unroll 1
+                    for (int gi = 0; gi < n_groups; ++gi) {
+                        const int buf = egrp & 1;
+                        uint8_t* sbuf = epi_stage + (q * 2 + buf) * 4096;
+                        if (out_col_base + gi * 64 >= a.n_feat) break;  // fully out-of-range group (warp-uniform)
+                        if (lane == 0) {
+                            if (tma_res) {
+                                bulk_wait_read<0>();  // store of the previous group has drained its buffer
+                                if (gi + 1 < n_groups && out_col_base + (gi + 1) * 64 < a.n_feat) {
+                                    mbar_arrive_expect_tx(&rbar[q * 2 + (buf ^ 1)], 4096);
+                                    tma_load_2d(epi_stage + (q * 2 + (buf ^ 1)) * 4096, &map_res, &rbar[q * 2 + (buf ^ 1)],
+                                                out_col_base + (gi + 1) * 64, row0);
+                                }
+                            } else {
+                                bulk_wait_read<1>();  // the store that last used THIS buffer has drained it
+                            }
+                        }
+                        __syncwarp();
+                        if (tma_res) {
+                            mbar_wait(&rbar[q * 2 + buf], buf ? rpar1 : rpar0);
+                            if (buf) rpar1 ^= 1; else rpar0 ^= 1;
+                        }
+                        uint8_t* srow = sbuf + lane * 128;
+#pragma unroll
+                        for (int half = 0; half < 2; ++half) {
+                            const int tcol = gi * 64 + half * 32;
+                            uint32_t v[32], u[32];
+                            tmem_ld32(taddr + tcol, v);
+                            if (swiglu) tmem_ld32(taddr + BN / 2 + tcol, u);
+                            tmem_ld_wait();
+                            const int f0 = out_col_base + tcol;
+                            float x[32];
+                            if (swiglu) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) x[j] = epi_swiglu(__uint_as_float(v[j]), __uint_as_float(u[j]));
+                            } else {
+                                float bsv[32], rs[32];
+                                if ((flags & EPI_BIAS) && f0 + 32 <= a.n_feat) {
+                                    const uint4* bp = reinterpret_cast<const uint4*>(a.bias + f0);
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        uint4 bv = __ldg(bp + j);
+                                        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&bv);
+#pragma unroll
+                                        for (int e = 0; e < 4; ++e) {
+                                            float2 f = __bfloat1622float2(h[e]);
+                                            bsv[j * 8 + e * 2] = f.x;
+                                            bsv[j * 8 + e * 2 + 1] = f.y;
+                                        }
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j)
+                                        bsv[j] = ((flags & EPI_BIAS) && f0 + j < a.n_feat) ? __bfloat162float(a.bias[f0 + j]) : 0.f;
+                                }
+                                if (tma_res) {
+#pragma unroll
+                                    for (int g4 = 0; g4 < 4; ++g4) {
+                                        const uint4 rv = *reinterpret_cast<const uint4*>(srow + (((half * 4 + g4) ^ (lane & 7)) << 4));
+                                        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                                        for (int e = 0; e < 4; ++e) {
+                                            float2 f = __bfloat1622float2(h[e]);
+                                            rs[g4 * 8 + e * 2] = f.x;
+                                            rs[g4 * 8 + e * 2 + 1] = f.y;
+                                        }
+                                    }
+                                } else if (flags & EPI_RESID) {  // periodic residual (positional embedding): direct loads
+                                    const bf16* rp = a.resid + static_cast<size_t>(res_row) * a.ld_res + f0;
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) rs[j] = (row_ok && f0 + j < a.n_feat) ? __bfloat162float(rp[j]) : 0.f;
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) rs[j] = 0.f;
+                                }
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) x[j] = epi_elem(__uint_as_float(v[j]), flags, bsv[j], rs[j]);
+                            }
+#pragma unroll
+                            for (int g4 = 0; g4 < 4; ++g4)
+                                *reinterpret_cast<uint4*>(srow + (((half * 4 + g4) ^ (lane & 7)) << 4)) =
+                                    make_uint4(pack_bf16x2(x[8 * g4], x[8 * g4 + 1]), pack_bf16x2(x[8 * g4 + 2], x[8 * g4 + 3]),
+                                               pack_bf16x2(x[8 * g4 + 4], x[8 * g4 + 5]), pack_bf16x2(x[8 * g4 + 6], x[8 * g4 + 7]));
+                        }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&map_out, sbuf, out_col_base + gi * 64, row0);
+                            bulk_commit();
+                        }
+                        ++egrp;
+                    }
+                } else if (flags & EPI_SWIGLU) {
                     // cols [0, BN/2) = gate, [BN/2, BN) = up of the same BN/2 output features
                     constexpr int HALF = BN / 2;
 #pragma unroll 1
@@ -311,6 +445,36 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
                     tmem_ld32(taddr + ch * 32, v);
                     if constexpr (NA == 2) tmem_ld32(taddr + BN + ch * 32, u);
                     tmem_ld_wait();
+                    if constexpr (NA == 1 && BN == 32) {
+                        if (k_splits > 1) {
+                            // publish this split's partial tile: ws[tile][split][col][row] (row fastest: coalesced)
+                            const int tile = t / k_splits, sp = t % k_splits;
+                            float* wt = a.ws + (static_cast<size_t>(tile) * k_splits) * (BN * 128);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) wt[(sp * BN + j) * 128 + row_in_tile] = __uint_as_float(v[j]);
+                            __threadfence();
+                            asm volatile("bar.sync 1, 128;" ::: "memory");
+                            if (threadIdx.x == 64) *reinterpret_cast<volatile int*>(tmem_slot + 1) = atomicAdd(a.counters + tile, 1);
+                            asm volatile("bar.sync 1, 128;" ::: "memory");
+                            const int arrived = *reinterpret_cast<volatile int*>(tmem_slot + 1);
+                            if (arrived != k_splits - 1) continue;  // not the last split of this tile: done
+                            __threadfence();
+                            // fixed split order (deterministic); 32 independent L2 loads in flight per round
+                            float sum[32];
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) sum[j] = 0.f;
+                            for (int s2 = 0; s2 < k_splits; ++s2) {
+                                float tmp[32];
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) tmp[j] = __ldcg(wt + (s2 * BN + j) * 128 + row_in_tile);
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) sum[j] += tmp[j];
+                            }
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(sum[j]);
+                            if (threadIdx.x == 64) a.counters[tile] = 0;
+                        }
+                    }
                     const int tok0 = c * BN + ch * 32;
                     if (feat_ok) {
 #pragma unroll
@@ -346,31 +510,61 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
         }
     }
 
+    if (!SWAP && warp >= 2 && lane == 0) bulk_wait_read<0>();  // staged tiles must be read out before smem goes away
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
-template <int BN, int NA, int STAGES, bool SWAP>
-static int launch(const CUtensorMap& mr, const CUtensorMap& mc, const GemmArgs& a, cudaStream_t stream) {
-    using Cfg = GemmCfg<BN, NA, STAGES>;
-    auto kern = gemm_kernel<BN, NA, STAGES, SWAP>;
+template <int BN, int NA, int STAGES, bool SWAP, int EPI>
+static int launch_epi(const CUtensorMap& mr, const CUtensorMap& mc, const CUtensorMap& mo, const CUtensorMap& mres,
+                  const GemmArgs& a, cudaStream_t stream) {
+    using Cfg = GemmCfg<BN, NA, STAGES, SWAP>;
+    auto kern = gemm_kernel<BN, NA, STAGES, SWAP, EPI>;
     static bool configured = false;
     if (!configured) {
         AF3_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         configured = true;
     }
-    const int tiles = a.num_r_tiles * a.num_c_tiles;
+    const int tiles = a.num_r_tiles * a.num_c_tiles * (SWAP && a.k_splits > 1 ? a.k_splits : 1);
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    kern<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(mr, mc, a);
+    kern<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(mr, mc, mo, mres, a);
     AF3_CHECK_LAUNCH();
     return 0;
 }
 
 // Host entry.  x: [n_tok, K] bf16 (pitch ldx), w: [n_rows_w, K] bf16 (pitch ldw) where n_rows_w = n_feat, or the
 // gate/up-interleaved 2*ceil(n_feat/128)*128 rows when EPI_SWIGLU.  out: [n_tok, n_feat] (pitch ldo).
+// compile-time epilogue specialisations for the flag sets the AF3 path uses; anything else -> generic (-1)
+template <int BN, int NA, int STAGES, bool SWAP>
+static int launch(const CUtensorMap& mr, const CUtensorMap& mc, const CUtensorMap& mo, const CUtensorMap& mres,
+                  const GemmArgs& a, cudaStream_t stream) {
+#define AF3_EPI_CASE(F) \
+    case (F):           \
+        return launch_epi<BN, NA, STAGES, SWAP, (F)>(mr, mc, mo, mres, a, stream);
+    if (SWAP || a.tma_epi) {
+        switch (a.flags) {
+            AF3_EPI_CASE(0)
+            AF3_EPI_CASE(EPI_BIAS)
+            AF3_EPI_CASE(EPI_BIAS | EPI_GELU)
+            AF3_EPI_CASE(EPI_BIAS | EPI_RESID)
+            AF3_EPI_CASE(EPI_RESID)
+            AF3_EPI_CASE(EPI_SWIGLU)
+            AF3_EPI_CASE(EPI_F32OUT)
+            AF3_EPI_CASE(EPI_BIAS | EPI_GELU | EPI_RESID)
+            default:
+                break;
+        }
+    }
+#undef AF3_EPI_CASE
+    return launch_epi<BN, NA, STAGES, SWAP, -1>(mr, mc, mo, mres, a, stream);
+}
+
+size_t gemm_workspace_bytes() { return (8u << 20) + 4096 * sizeof(int); }
+
 int gemm_bf16(cudaStream_t stream, const bf16* x, int ldx, const bf16* w, int ldw, void* out, int ldo, int n_tok,
-              int n_feat, int K, int flags, const bf16* bias, const bf16* resid, int ld_res, int res_period) {
+              int n_feat, int K, int flags, const bf16* bias, const bf16* resid, int ld_res, int res_period,
+              void* workspace, size_t workspace_bytes) {
     AF3_REQUIRE(n_tok > 0 && n_feat > 0 && K > 0, "gemm: empty problem");
     AF3_REQUIRE((K % 8) == 0 && (ldx % 8) == 0 && (ldw % 8) == 0, "gemm: K and pitches must be multiples of 8");
     AF3_REQUIRE(!(flags & EPI_BIAS) || bias, "gemm: bias flag without pointer");
@@ -388,7 +582,8 @@ int gemm_bf16(cudaStream_t stream, const bf16* x, int ldx, const bf16* w, int ld
     a.ld_res = ld_res;
     a.res_period = res_period;
     a.flags = flags;
-    CUtensorMap mx, mw;
+    a.k_splits = 1;
+    CUtensorMap mx, mw, mo, mres;
     const bool swap = n_tok <= 64;
     if (!swap) {
         constexpr int BN = 256;
@@ -396,10 +591,27 @@ int gemm_bf16(cudaStream_t stream, const bf16* x, int ldx, const bf16* w, int ld
         a.C = w_rows;
         a.num_r_tiles = ceil_div(n_tok, 128);
         a.num_c_tiles = ceil_div(w_rows, BN);
-        a.group_r = 16;
+        // rasterisation: GROUP_R row tiles stay L2-resident (~48 MB of the 126 MB L2) while the col-operand tiles stream
+        // past them, so the streamed operand is re-read num_r_tiles / GROUP_R times instead of once per row tile
+        {
+            const long long tile_bytes = 128ll * K * 2;
+            long long g = (48ll << 20) / tile_bytes;
+            a.group_r = static_cast<int>(g < 8 ? 8 : (g > 256 ? 256 : g));
+        }
         if (int e = make_tmap_2d(&mx, x, K, n_tok, ldx, BK, 128)) return e;
         if (int e = make_tmap_2d(&mw, w, K, w_rows, ldw, BK, BN)) return e;
-        return launch<BN, 1, 4, false>(mx, mw, a, stream);
+        // smem-staged TMA-store epilogue whenever the output (and residual) layout allows 16-byte-aligned rows
+        const bool res_plain = (flags & EPI_RESID) && res_period == 0;
+        a.tma_epi = !(flags & EPI_F32OUT) && (ldo % 8 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) &&
+                    (!res_plain || ((ld_res % 8 == 0) && ((reinterpret_cast<uintptr_t>(resid) & 15) == 0)));
+        mo = mx;
+        mres = mx;
+        if (a.tma_epi) {
+            if (int e = make_tmap_2d(&mo, out, n_feat, n_tok, ldo, 64, 32)) return e;
+            if (res_plain)
+                if (int e = make_tmap_2d(&mres, resid, n_feat, n_tok, ld_res, 64, 32)) return e;
+        }
+        return launch<BN, 1, 4, false>(mx, mw, mo, mres, a, stream);
     }
     constexpr int BN = 32;
     a.R = w_rows;
@@ -410,10 +622,24 @@ int gemm_bf16(cudaStream_t stream, const bf16* x, int ldx, const bf16* w, int ld
     if (int e = make_tmap_2d(&mx, x, K, n_tok, ldx, BK, BN)) return e;
     if (swiglu) {
         a.num_r_tiles = ceil_div(w_rows, 256);
-        return launch<BN, 2, 6, true>(mw, mx, a, stream);
+        return launch<BN, 2, 6, true>(mw, mx, mw, mw, a, stream);
     }
     a.num_r_tiles = ceil_div(w_rows, 128);
-    return launch<BN, 1, 8, true>(mw, mx, a, stream);
+    // split-K when the tile grid cannot fill the GPU and a (zero-initialised) workspace was supplied
+    a.k_splits = 1;
+    const int tiles = a.num_r_tiles * a.num_c_tiles;
+    const int kb_total = ceil_div(K, BK);
+    if (workspace && workspace_bytes >= gemm_workspace_bytes() && tiles * 2 <= sm_count() && tiles <= 4096) {
+        int s = sm_count() / tiles;
+        if (s > kb_total / 4) s = kb_total / 4;  // keep at least 4 k-blocks per split
+        if (s > 16) s = 16;
+        if (s >= 2 && static_cast<size_t>(tiles) * s * BN * 128 * sizeof(float) <= (8u << 20)) {
+            a.k_splits = s;
+            a.ws = reinterpret_cast<float*>(workspace);
+            a.counters = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(workspace) + (8u << 20));
+        }
+    }
+    return launch<BN, 1, 8, true>(mw, mx, mw, mw, a, stream);
 }
 
 }  // namespace af3

@@ -467,7 +467,7 @@ class AudioFlamingo3ForConditionalGeneration(nn.Module):
                 raise AF3Error("cached forward expects exactly one new token per sequence")
             B = input_ids.shape[0]
             x, _ = ops.embed_scatter(input_ids.to(dev).reshape(-1).contiguous(), lm.model.embed_tokens.weight, -1, None, 0, 1, None)
-            scratch = ops.decode_attention_scratch(B, lm.H, lm.D, dev)
+            scratch = ops.decode_attention_scratch(B, lm.H, lm.D, past_key_values.Tmax, dev)
             logits = lm.decode_step(x, past_key_values, scratch)
             past_key_values.length += 1
             return CausalLMOutputWithPast(logits=logits.view(B, 1, -1), past_key_values=past_key_values)
@@ -541,7 +541,7 @@ class AudioFlamingo3ForConditionalGeneration(nn.Module):
         lm = self.language_model
         dev = lm.lm_head.weight.device
         table = lm.model.embed_tokens.weight
-        scratch = ops.decode_attention_scratch(B, lm.H, lm.D, dev)
+        scratch = ops.decode_attention_scratch(B, lm.H, lm.D, cache.Tmax, dev)
         ids_buf = torch.zeros((B,), device=dev, dtype=torch.int64)
 
         def eager(next_ids):

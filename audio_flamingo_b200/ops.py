@@ -56,6 +56,19 @@ def _req(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
 
 
 # ----------------------------------------------------------------------------------------------- GEMM
+_WORKSPACES = {}
+
+
+def gemm_workspace(device):
+    """Zero-initialised split-K workspace, one per device (GEMMs on a stream are serialised, so it is shared)."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    ws = _WORKSPACES.get(key)
+    if ws is None:
+        ws = torch.zeros((_lib.load().af3_gemm_workspace_bytes(),), device=torch.device("cuda", key), dtype=torch.uint8)
+        _WORKSPACES[key] = ws
+    return ws
+
+
 def linear(x, w, bias=None, *, gelu=False, resid=None, res_period=0, out=None, out_f32=False):
     """out = epi(x @ w.T); x [n_tok, K] bf16, w [n_feat, K] bf16 (nn.Linear layout)."""
     lib = _lib.load()
@@ -75,10 +88,12 @@ def linear(x, w, bias=None, *, gelu=False, resid=None, res_period=0, out=None, o
         flags |= EPI_F32OUT
     if out is None:
         out = torch.empty((n_tok, n_feat), device=x.device, dtype=torch.float32 if out_f32 else bf16)
+    ws = gemm_workspace(x.device) if n_tok <= 64 else None
     with _Timed(("gemm", n_tok, n_feat, K, flags)):
         check(
-            lib.af3_gemm_bf16(stream_ptr(), ptr(x), x.stride(0), ptr(w), w.stride(0), ptr(out), out.stride(0), n_tok, n_feat,
-                              K, flags, ptr(bias), ptr(resid), resid.stride(0) if resid is not None else 0, res_period),
+            lib.af3_gemm_bf16_ws(stream_ptr(), ptr(x), x.stride(0), ptr(w), w.stride(0), ptr(out), out.stride(0), n_tok, n_feat,
+                                 K, flags, ptr(bias), ptr(resid), resid.stride(0) if resid is not None else 0, res_period,
+                                 ptr(ws), ws.numel() if ws is not None else 0),
             "af3_gemm_bf16",
         )
     _count(1)
@@ -249,8 +264,8 @@ def decode_attention(qkv, k_cache, v_cache, out, scratch, *, B, H, Hkv, D, ctx_l
     return out
 
 
-def decode_attention_scratch(B, H, D, device):
-    n = _lib.load().af3_decode_attention_scratch_bytes(B, H, D)
+def decode_attention_scratch(B, H, D, Tmax, device):
+    n = _lib.load().af3_decode_attention_scratch_bytes(B, H, D, Tmax)
     return torch.empty((n // 4,), device=device, dtype=torch.float32)
 
 

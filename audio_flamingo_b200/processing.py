@@ -58,6 +58,24 @@ def expand_audio_tokens(ids: list[int], audio_token_id: int, n_tokens: int) -> l
     return out
 
 
+def expand_audio_spans(ids: list[int], audio_token_id: int, counts: list[int]) -> list[int]:
+    """Multi-audio prompts (AF3-Chat): the i-th <sound> placeholder becomes counts[i] audio tokens.
+    The reference processor enforces one audio per text and one count for every placeholder ([O] AF3P:155-156, 98-100);
+    the model side (masked_scatter, AF3M:563-566) already accepts any layout, so only this expansion is new."""
+    out, k = [], 0
+    for t in ids:
+        if t == audio_token_id:
+            if k >= len(counts):
+                raise ValueError("more <sound> placeholders than audio clips")
+            out.extend([audio_token_id] * counts[k])
+            k += 1
+        else:
+            out.append(t)
+    if k != len(counts):
+        raise ValueError("fewer <sound> placeholders than audio clips")
+    return out
+
+
 def left_pad(rows: list[list[int]], pad_id: int = 0):
     """Tokenizer padding_side='left' ([O] AF3P:44-47) -> (input_ids, attention_mask) int64 tensors."""
     S = max(len(r) for r in rows)

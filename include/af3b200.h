@@ -37,6 +37,15 @@ int af3_abi_version(void);
 int af3_gemm_bf16(void* stream, const void* x, int ldx, const void* w, int ldw, void* out, int ldo, int n_tok,
                   int n_feat, int K, int flags, const void* bias, const void* resid, int ld_res, int res_period);
 
+/* Same, with a caller-provided ZERO-INITIALISED device workspace of af3_gemm_workspace_bytes() bytes (reusable across
+ * calls on one stream; the kernel leaves it zeroed where it matters).  With it, few-token GEMMs whose weight matrix
+ * has too few 128-row tiles to fill the GPU (decode-step q/k/v, o and down projections) are split along K across
+ * CTAs and reduced deterministically by the last-arriving CTA of each tile. */
+size_t af3_gemm_workspace_bytes(void);
+int af3_gemm_bf16_ws(void* stream, const void* x, int ldx, const void* w, int ldw, void* out, int ldo, int n_tok,
+                     int n_feat, int K, int flags, const void* bias, const void* resid, int ld_res, int res_period,
+                     void* workspace, size_t workspace_bytes);
+
 /* gate [F,K], up [F,K] -> packed [2*ceil(F/128)*128, K]: per 128 features, 128 gate rows then 128 up rows. */
 int af3_pack_gate_up(void* stream, const void* gate, const void* up, void* packed, int F, int K);
 
@@ -89,7 +98,7 @@ int af3_rope_kv_append(void* stream, void* qkv, void* k_cache, void* v_cache, in
 int af3_decode_attention(void* stream, const void* qkv, const void* k_cache, const void* v_cache, void* out,
                          float* scratch, int B, int H, int Hkv, int D, int Tmax, const int* ctx_len,
                          const int* kv_start, float scale);
-size_t af3_decode_attention_scratch_bytes(int B, int H, int D);
+size_t af3_decode_attention_scratch_bytes(int B, int H, int D, int Tmax);
 
 /* Token embedding gather + audio-row scatter (AF3M:557, 563-566 masked_scatter).
  * ids int64 [n_tok]; audio rows taken in order from audio_embeds [n_win*frames, dim] keeping the first

@@ -8,7 +8,7 @@ import pytest
 import torch
 from hypothesis import given, settings, strategies as st
 
-from audio_flamingo_b200.processing import expand_audio_tokens, left_pad, split_windows
+from audio_flamingo_b200.processing import expand_audio_spans, expand_audio_tokens, left_pad, split_windows
 from audio_flamingo_b200.sharding import gather_tokens, shard_rows
 
 
@@ -72,6 +72,9 @@ def test_prompt_helpers():
     assert ids == [5, 9, 9, 9, 9, 7]
     a, m = left_pad([[1, 2, 3], [4]], pad_id=0)
     assert a.tolist() == [[1, 2, 3], [0, 0, 4]] and m.tolist() == [[1, 1, 1], [0, 0, 1]]
+    assert expand_audio_spans([1, 9, 2, 9, 3], 9, [2, 3]) == [1, 9, 9, 2, 9, 9, 9, 3]
+    with pytest.raises(ValueError):
+        expand_audio_spans([1, 9, 2], 9, [2, 3])
     chunks, per = split_windows([np.zeros(480000 * 25, np.float32)])
     assert per == [20] and len(chunks) == 20  # 600 s cap (AF3P:82,160)
 

@@ -44,12 +44,28 @@ def test_gemm_plain(ops, M, N, K):
 
 
 @pytest.mark.parametrize("M", [1, 7, 32, 33, 64])
-@pytest.mark.parametrize("N,K", [(256, 128), (3584, 512), (200, 64)])
+@pytest.mark.parametrize("N,K", [(256, 128), (3584, 512), (200, 64), (3584, 3584), (512, 4096)])  # the last three take the split-K path
 def test_gemm_swap_small_m(ops, M, N, K):
     x, w, b = _rand((M, K), 1.0, 3), _rand((N, K), 0.05, 4), _rand((N,), 0.5, 5)
     out = ops.linear(x, w, b)
     ref = (x.float() @ w.float().T + b.float()).to(bf16)
     _close(out, ref, BF16_RTOL, 1e-3, f"swap gemm {M}x{N}x{K}")
+
+
+def test_gemm_splitk_deterministic_and_epilogue(ops):
+    """Decode-shaped GEMM (32 tokens, 3584 x 18944 down projection + residual): split-K partials are reduced in a fixed
+    order by the last CTA, so repeated launches are bit-identical; result matches the fp32 restatement."""
+    M, N, K = 32, 3584, 18944
+    x, w, res = _rand((M, K), 1.0, 14), _rand((N, K), 0.02, 15), _rand((M, N), 1.0, 16)
+    outs = [ops.linear(x, w, resid=res) for _ in range(5)]
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    lin = (x.float() @ w.float().T).to(bf16).float()
+    ref = (lin + res.float()).to(bf16)
+    # one bf16 ulp of the (larger) linear output may survive the residual add even where lin + res cancels
+    err = (outs[0].float() - ref.float()).abs()
+    tol = 4e-3 + BF16_RTOL * (lin.abs() + res.float().abs())
+    assert (err <= tol).all(), f"max err {err.max().item()}"
 
 
 @pytest.mark.parametrize("M", [16, 640])
@@ -249,7 +265,7 @@ def test_decode_attention(ops):
     starts = torch.tensor([0, 100, 776], dtype=torch.int32, device="cuda")
     ctx_len = torch.tensor([ctx], dtype=torch.int32, device="cuda")
     out = torch.zeros((B, H * D), device="cuda", dtype=bf16)
-    scratch = ops.decode_attention_scratch(B, H, D, "cuda")
+    scratch = ops.decode_attention_scratch(B, H, D, Tmax, "cuda")
     ops.decode_attention(qkv, k_cache, v_cache, out, scratch, B=B, H=H, Hkv=Hkv, D=D, ctx_len=ctx_len, kv_start=starts, scale=D ** -0.5)
     q = qkv[:, :H * D].float().view(B, H, 1, D)
     k = k_cache[:, :, :ctx].float().repeat_interleave(H // Hkv, dim=1)

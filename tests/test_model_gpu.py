@@ -105,3 +105,41 @@ def test_feature_extractor_matches_reference(O):
     err = (out["input_features"].cpu() - feats).abs().max().item()
     print("logmel vs WhisperFeatureExtractor max abs err", err)
     assert err < 1e-4
+
+
+def test_multi_window_and_multi_audio_prompts(O):
+    """a 45 s clip (2 windows) and a prompt with two separate <sound> spans; logits vs the HF
+    reference in bf16 on the same GPU and vs fp32 (the model side of the reference accepts any placeholder layout)."""
+    from audio_flamingo_b200 import AF3FeatureExtractor, AudioFlamingo3ForConditionalGeneration
+    from audio_flamingo_b200.processing import audio_token_length, expand_audio_spans, left_pad, split_windows, tokens_per_sample
+
+    ref32 = O.hf_model("tiny", seed=0, sharpen=8.0)
+    cfg = ref32.config
+    aid, V = cfg.audio_token_id, cfg.text_config.vocab_size
+    clips = O.synth_waveforms(3, [45.0, 6.0, 2.5], seed=21)
+    chunks, per = split_windows(clips)                      # [30 s, 15 s], [6 s], [2.5 s]
+    assert per == [2, 1, 1]
+    fe = AF3FeatureExtractor("cuda")
+    fo = fe(chunks, sampling_rate=16000)
+    frames = fo["attention_mask"].sum(-1).cpu().tolist()
+    rs = np.random.RandomState(3)
+    # sample 0: one <sound> for its two windows (processor semantics: summed frames); sample 1: two clips, two spans
+    n0 = tokens_per_sample(frames[:2], [2])[0]
+    n1a, n1b = int(audio_token_length(frames[2])), int(audio_token_length(frames[3]))
+    t = lambda n: rs.randint(1, V - 2, size=n).tolist()
+    row0 = expand_audio_spans(t(4) + [aid] + t(9), aid, [n0])
+    row1 = expand_audio_spans(t(3) + [aid] + t(5) + [aid] + t(7), aid, [n1a, n1b])
+    ids, am = left_pad([row0, row1])
+    feats_ref, fmask_ref = O.hf_features(chunks)
+    ours = AudioFlamingo3ForConditionalGeneration.from_reference(ref32, device="cuda")
+    with torch.no_grad():
+        l32 = ref32(input_ids=ids, attention_mask=am, input_features=feats_ref, input_features_mask=fmask_ref).logits
+    lo = ours(input_ids=ids.cuda(), attention_mask=am.cuda(), input_features=fo["input_features"],
+              input_features_mask=fo["input_features_mask"]).logits.float().cpu()
+    v = am.bool()
+    assert (lo - l32)[v].abs().max().item() < 0.06 * l32[v].std().item()
+    # a prompt whose placeholder count does not match the features must raise like the reference's masked_scatter
+    bad = ids.clone()
+    bad[0, -1] = aid
+    with pytest.raises(ValueError):
+        ours(input_ids=bad.cuda(), attention_mask=am.cuda(), input_features=fo["input_features"], input_features_mask=fo["input_features_mask"])
