@@ -18,6 +18,7 @@ _p, _i, _f, _i64, _sz = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_size_t
 SIGNATURES = {
     "af3_last_error": (C.c_char_p, []),
     "af3_abi_version": (_i, []),
+    "af3_set_pdl": (None, [_i]),
     "af3_gemm_bf16": (_i, [_p, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _p, _p, _i, _i]),
     "af3_gemm_workspace_bytes": (_sz, []),
     "af3_gemm_bf16_ws": (_i, [_p, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p, _sz]),
@@ -33,7 +34,8 @@ SIGNATURES = {
     "af3_decode_attention": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _f]),
     "af3_decode_attention_scratch_bytes": (_sz, [_i, _i, _i, _i]),
     "af3_embed_scatter": (_i, [_p, _p, _i, _p, _i, _i64, _p, _i, _i, _p, _p, _p, _p]),
-    "af3_argmax": (_i, [_p, _p, _i, _i, _p]),
+    "af3_argmax_scratch_bytes": (_sz, [_i]),
+    "af3_argmax": (_i, [_p, _p, _i, _i, _p, _p]),
 }
 
 _lib = None

@@ -21,7 +21,8 @@ int rope_kv_append(cudaStream_t, bf16*, bf16*, bf16*, int, int, int, int, int, i
                    const float*);
 int embed_scatter(cudaStream_t, const int64_t*, int, const bf16*, int, int64_t, const bf16*, int, int, const int*, bf16*,
                   int*, int*);
-int argmax(cudaStream_t, const float*, int, int, int64_t*);
+int argmax(cudaStream_t, const float*, int, int, int64_t*, void*);
+size_t argmax_scratch_bytes(int B);
 int attention(cudaStream_t stream, const bf16* q, int ldq, const bf16* k, const bf16* v, int ldk, int kv_layout,
               int Tk_pitch, bf16* out, int ldo, int B, int H, int Hkv, int D, int Tq, int Tk, float scale, int causal,
               const int* kv_len, const int* kv_start);
@@ -40,6 +41,7 @@ extern "C" {
 
 const char* af3_last_error(void) { return af3::last_error_cstr(); }
 int af3_abi_version(void) { return 1; }
+void af3_set_pdl(int enable) { af3::set_pdl(enable != 0); }
 
 int af3_gemm_bf16(void* stream, const void* x, int ldx, const void* w, int ldw, void* out, int ldo, int n_tok, int n_feat,
                   int K, int flags, const void* bias, const void* resid, int ld_res, int res_period) {
@@ -115,8 +117,9 @@ int af3_embed_scatter(void* stream, const int64_t* ids, int n_tok, const void* e
                               frames, post_len, B16M(out), scratch_rows, counts);
 }
 
-int af3_argmax(void* stream, const float* logits, int B, int V, int64_t* out_ids) {
-    return af3::argmax(S(stream), logits, B, V, out_ids);
+size_t af3_argmax_scratch_bytes(int B) { return af3::argmax_scratch_bytes(B); }
+int af3_argmax(void* stream, const float* logits, int B, int V, int64_t* out_ids, void* scratch) {
+    return af3::argmax(S(stream), logits, B, V, out_ids, scratch);
 }
 
 }  // extern "C"

@@ -65,6 +65,10 @@ int make_tmap_3d(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, u
     return encode(map, base, 3, dims, strides, box);
 }
 
+static bool g_pdl = false;
+bool pdl_enabled() { return g_pdl; }
+void set_pdl(bool on) { g_pdl = on; }
+
 int sm_count() {
     static int n = 0;
     if (n == 0) {

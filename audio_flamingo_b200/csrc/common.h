@@ -40,6 +40,28 @@ int make_tmap_3d(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, u
 
 int sm_count();
 
+// Programmatic dependent launch for the decode-step kernel chain (af3_set_pdl).  launch_kernel() adds the
+// cudaLaunchAttributeProgrammaticStreamSerialization attribute when enabled; every kernel launched through it calls
+// pdl_wait() before touching data produced by earlier kernels.
+bool pdl_enabled();
+void set_pdl(bool on);
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 }  // namespace af3

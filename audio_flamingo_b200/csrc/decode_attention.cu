@@ -25,6 +25,8 @@ decode_attn_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ k_cach
     const int G = H / Hkv;
     const int b = blockIdx.x, hk = blockIdx.y, sp = blockIdx.z;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_launch_dependents();
+    pdl_wait();
     const int ctx = *ctx_len_p;
     const int start = kv_start ? kv_start[b] : 0;
     const int j0 = sp * DA_CHUNK;
@@ -56,9 +58,12 @@ decode_attn_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ k_cach
     for (int g = 0; g < DA_MAXG; ++g) s[g] = 0.f;
     if (valid) {
         const uint4* kp = reinterpret_cast<const uint4*>(k_cache + ((static_cast<size_t>(b) * Hkv + hk) * Tmax + j) * D);
-#pragma unroll 4
+        uint4 kreg[D / 8];
+#pragma unroll
+        for (int c = 0; c < D / 8; ++c) kreg[c] = __ldg(kp + c);  // the whole 256-byte K row in flight at once
+#pragma unroll
         for (int c = 0; c < D / 8; ++c) {
-            const uint4 kv = __ldg(kp + c);
+            const uint4 kv = kreg[c];
             const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&kv);
             float kf[8];
 #pragma unroll
@@ -99,22 +104,64 @@ decode_attn_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ k_cach
         if (lane == 0) red_l[g][warp] = ps;
     }
     __syncthreads();
-    // ---- P.V: thread = output dim
-    float o_acc[DA_MAXG];
+    // ---- P.V: warp w takes keys jj = w, w+4, ...; lane owns dims 4*lane .. 4*lane+3 (8-byte loads, a warp reads a whole
+    //      256-byte V row); 8 independent row loads in flight per warp; cross-warp reduction through shared memory
+    float o_acc[DA_MAXG][4];
 #pragma unroll
-    for (int g = 0; g < DA_MAXG; ++g) o_acc[g] = 0.f;
-    const bf16* vbase = v_cache + ((static_cast<size_t>(b) * Hkv + hk) * Tmax + j0) * D + tid;
+    for (int g = 0; g < DA_MAXG; ++g)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o_acc[g][e] = 0.f;
+    const bf16* vbase = v_cache + ((static_cast<size_t>(b) * Hkv + hk) * Tmax + j0) * D + lane * 4;
     const int jj0 = j_beg - j0, jj1 = j_end - j0;
-#pragma unroll 4
-    for (int jj = jj0; jj < jj1; ++jj) {
-        const float v = __bfloat162float(vbase[static_cast<size_t>(jj) * D]);
+    for (int jb = jj0 + warp; jb < jj1; jb += 4 * 8) {
+        uint2 vv[8];
 #pragma unroll
-        for (int g = 0; g < DA_MAXG; ++g)
-            if (g < G) o_acc[g] = fmaf(p_s[g][jj], v, o_acc[g]);
+        for (int u = 0; u < 8; ++u) {
+            const int jj = jb + 4 * u;
+            vv[u] = (jj < jj1) ? __ldg(reinterpret_cast<const uint2*>(vbase + static_cast<size_t>(jj) * D)) : make_uint2(0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int jj = jb + 4 * u;
+            if (jj < jj1) {
+                const float2 va = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&vv[u].x));
+                const float2 vb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&vv[u].y));
+#pragma unroll
+                for (int g = 0; g < DA_MAXG; ++g) {
+                    if (g < G) {
+                        const float p = p_s[g][jj];
+                        o_acc[g][0] = fmaf(p, va.x, o_acc[g][0]);
+                        o_acc[g][1] = fmaf(p, va.y, o_acc[g][1]);
+                        o_acc[g][2] = fmaf(p, vb.x, o_acc[g][2]);
+                        o_acc[g][3] = fmaf(p, vb.y, o_acc[g][3]);
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();  // q_s is dead from here: reuse it as the cross-warp reduction buffer [warp][G*D] (G*D <= 1024 floats)
+    float* red = &q_s[0][0];
+    // four passes (one per warp) keep the buffer at G*D floats: warp w adds its partial in turn
+    for (int w = 0; w < 4; ++w) {
+        if (warp == w) {
+#pragma unroll
+            for (int g = 0; g < DA_MAXG; ++g) {
+                if (g < G) {
+                    float4* dst = reinterpret_cast<float4*>(red + g * D + lane * 4);
+                    float4 cur = (w == 0) ? make_float4(0.f, 0.f, 0.f, 0.f) : *dst;
+                    cur.x += o_acc[g][0];
+                    cur.y += o_acc[g][1];
+                    cur.z += o_acc[g][2];
+                    cur.w += o_acc[g][3];
+                    *dst = cur;
+                }
+            }
+        }
+        __syncthreads();
     }
     for (int g = 0; g < G; ++g) {
         float* dst = pbase + static_cast<size_t>(g) * nsplit * (D + 2);
-        dst[tid] = o_acc[g];
+        dst[tid] = red[g * D + tid];
         if (tid == 0) {
             dst[D] = m_c[g];
             dst[D + 1] = red_l[g][0] + red_l[g][1] + red_l[g][2] + red_l[g][3];
@@ -126,6 +173,8 @@ template <int D>
 __global__ void __launch_bounds__(D)
 decode_attn_combine(const float* __restrict__ part, bf16* __restrict__ out, int H, int nsplit) {
     const int b = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
     const float* src = part + (static_cast<size_t>(b) * H + h) * nsplit * (D + 2);
     float m = -INFINITY;
     for (int s = 0; s < nsplit; ++s) m = fmaxf(m, src[s * (D + 2) + D]);
@@ -155,12 +204,10 @@ int decode_attention(cudaStream_t stream, const bf16* qkv, const bf16* k_cache, 
     const int ns = n_splits(Tmax);
     AF3_REQUIRE(ns <= 65535, "decode_attention: context too long");
     dim3 grid(B, Hkv, ns);
-    decode_attn_kernel<128><<<grid, DA_THREADS, 0, stream>>>(qkv, k_cache, v_cache, scratch, H, Hkv, Tmax, ns, ctx_len,
-                                                            kv_start, scale);
-    AF3_CHECK_LAUNCH();
+    AF3_CHECK_CUDA(launch_kernel(decode_attn_kernel<128>, grid, dim3(DA_THREADS), 0, stream, qkv, k_cache, v_cache, scratch, H,
+                                 Hkv, Tmax, ns, ctx_len, kv_start, scale));
     dim3 g2(B, H);
-    decode_attn_combine<128><<<g2, 128, 0, stream>>>(scratch, out, H, ns);
-    AF3_CHECK_LAUNCH();
+    AF3_CHECK_CUDA(launch_kernel(decode_attn_combine<128>, g2, dim3(128), 0, stream, static_cast<const float*>(scratch), out, H, ns));
     return 0;
 }
 

@@ -116,6 +116,8 @@ int avgpool_layernorm(cudaStream_t stream, const bf16* x, bf16* y, const bf16* g
 __global__ void __launch_bounds__(256)
 rmsnorm_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const bf16* __restrict__ weight, int rows, int dim,
                float eps, const int* __restrict__ row_idx) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -153,8 +155,8 @@ int rmsnorm(cudaStream_t stream, const bf16* x, bf16* y, const bf16* weight, int
             const int* row_idx) {
     AF3_REQUIRE(dim % 8 == 0 && dim <= NORM_MAXV * 256, "rmsnorm: dim must be a multiple of 8 and <= 4096");
     if (rows <= 0) return 0;
-    rmsnorm_kernel<<<ceil_div(rows, 8), 256, 0, stream>>>(x, y, weight, rows, dim, eps, row_idx);
-    AF3_CHECK_LAUNCH();
+    AF3_CHECK_CUDA(launch_kernel(rmsnorm_kernel, dim3(ceil_div(rows, 8)), dim3(256), 0, stream, x, y, weight, rows, dim, eps,
+                                 row_idx));
     return 0;
 }
 
@@ -273,6 +275,8 @@ rope_kv_append_kernel(bf16* __restrict__ qkv, bf16* __restrict__ k_cache, bf16* 
     const int cpt = half >> 3;  // 8-wide chunks per token half
     const int heads = H + 2 * Hkv;
     const long long total = static_cast<long long>(B) * T * cpt;
+    pdl_launch_dependents();
+    pdl_wait();
     const int p0 = pos0_dev ? *pos0_dev : pos0;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -323,9 +327,8 @@ int rope_kv_append(cudaStream_t stream, bf16* qkv, bf16* k_cache, bf16* v_cache,
     const long long total = static_cast<long long>(B) * T * (D / 16);
     if (total <= 0) return 0;
     const int grid = static_cast<int>(((total + 255) / 256) < 148ll * 32 ? ((total + 255) / 256) : 148ll * 32);
-    rope_kv_append_kernel<<<grid, 256, 0, stream>>>(qkv, k_cache, v_cache, B, T, H, Hkv, D, Tmax, pos0, pos0_dev, kv_start,
-                                                   inv_freq);
-    AF3_CHECK_LAUNCH();
+    AF3_CHECK_CUDA(launch_kernel(rope_kv_append_kernel, dim3(grid), dim3(256), 0, stream, qkv, k_cache, v_cache, B, T, H, Hkv, D,
+                                 Tmax, pos0, pos0_dev, kv_start, inv_freq));
     return 0;
 }
 
@@ -339,6 +342,8 @@ scatter_index_kernel(const int64_t* __restrict__ ids, int n_tok, int64_t audio_i
     __shared__ int warp_tot[32];
     __shared__ int carry;
     __shared__ int win_base[1025];
+    pdl_launch_dependents();
+    pdl_wait();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // window prefix (n_win <= 1024 handled in one sweep; larger handled serially by thread 0)
     if (tid == 0) {
@@ -398,6 +403,8 @@ scatter_index_kernel(const int64_t* __restrict__ ids, int n_tok, int64_t audio_i
 __global__ void __launch_bounds__(256)
 embed_scatter_kernel(const int64_t* __restrict__ ids, int n_tok, const bf16* __restrict__ table, int dim,
                      const bf16* __restrict__ audio, const int* __restrict__ src_row, bf16* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= n_tok) return;
@@ -416,72 +423,90 @@ int embed_scatter(cudaStream_t stream, const int64_t* ids, int n_tok, const bf16
     if (n_tok <= 0) return 0;
     static const int zero_len = 0;
     (void)zero_len;
-    scatter_index_kernel<<<1, 1024, 0, stream>>>(ids, n_tok, audio_id, post_len, n_win, frames, src_row_scratch, counts);
-    AF3_CHECK_LAUNCH();
-    embed_scatter_kernel<<<ceil_div(n_tok, 8), 256, 0, stream>>>(ids, n_tok, table, dim, audio, src_row_scratch, out);
-    AF3_CHECK_LAUNCH();
+    AF3_CHECK_CUDA(launch_kernel(scatter_index_kernel, dim3(1), dim3(1024), 0, stream, ids, n_tok, audio_id, post_len, n_win,
+                                 frames, src_row_scratch, counts));
+    AF3_CHECK_CUDA(launch_kernel(embed_scatter_kernel, dim3(ceil_div(n_tok, 8)), dim3(256), 0, stream, ids, n_tok, table, dim,
+                                 audio, src_row_scratch, out));
     return 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // Greedy argmax over fp32 logits ([O] GEN:2762 logits.float(), :2793 torch.argmax -> first maximal index).
-__global__ void __launch_bounds__(1024)
-argmax_kernel(const float* __restrict__ logits, int V, int64_t* __restrict__ out) {
-    const float* p = logits + static_cast<size_t>(blockIdx.x) * V;
+// Two stages so that the 19.5 MB of logits at batch 32 are read by B x 32 CTAs (not B): stage 1 reduces a slice of the
+// row to (max, first index), stage 2 merges the 32 slices.  NaNs are ignored; an all-NaN row yields 0.
+constexpr int AM_SPLIT = 32;
+
+__device__ __forceinline__ void argmax_merge(float& best, int& bi, float ob, int oi) {
+    if (ob > best || (ob == best && oi < bi)) {
+        best = ob;
+        bi = oi;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+argmax_partial_kernel(const float* __restrict__ logits, int V, float* __restrict__ pmax, int* __restrict__ pidx) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int row = blockIdx.x, sp = blockIdx.y;
+    const float* p = logits + static_cast<size_t>(row) * V;
+    const int per = ((V + AM_SPLIT - 1) / AM_SPLIT + 3) & ~3;  // slice length, multiple of 4
+    const int beg = sp * per, end = min(V, beg + per);
     float best = -INFINITY;
     int bi = 0x7fffffff;
-    const int n4 = ((reinterpret_cast<uintptr_t>(p) & 15) == 0) ? V / 4 : 0;
-    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
-        const float4 v = reinterpret_cast<const float4*>(p)[i];
-        const float e[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (e[j] > best || (e[j] == best && 4 * i + j < bi)) {
-                best = e[j];
-                bi = 4 * i + j;
-            }
-    }
-    for (int i = n4 * 4 + threadIdx.x; i < V; i += blockDim.x)
-        if (p[i] > best || (p[i] == best && i < bi)) {
-            best = p[i];
-            bi = i;
+    const bool vec = (reinterpret_cast<uintptr_t>(p) & 15) == 0;
+    if (vec) {
+        const int n4 = max(end - beg, 0) / 4;
+        const float4* p4 = reinterpret_cast<const float4*>(p + beg);
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+            const float4 v = __ldg(p4 + i);
+            const int base = beg + 4 * i;
+            argmax_merge(best, bi, v.x, base);
+            argmax_merge(best, bi, v.y, base + 1);
+            argmax_merge(best, bi, v.z, base + 2);
+            argmax_merge(best, bi, v.w, base + 3);
         }
-    __shared__ float sb[32];
-    __shared__ int si[32];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ob > best || (ob == best && oi < bi)) {
-            best = ob;
-            bi = oi;
-        }
+        for (int i = beg + n4 * 4 + threadIdx.x; i < end; i += blockDim.x) argmax_merge(best, bi, p[i], i);
+    } else {
+        for (int i = beg + threadIdx.x; i < end; i += blockDim.x) argmax_merge(best, bi, p[i], i);
     }
+    __shared__ float sb[8];
+    __shared__ int si[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) argmax_merge(best, bi, __shfl_xor_sync(0xffffffffu, best, o), __shfl_xor_sync(0xffffffffu, bi, o));
     if ((threadIdx.x & 31) == 0) {
         sb[threadIdx.x >> 5] = best;
         si[threadIdx.x >> 5] = bi;
     }
     __syncthreads();
-    if (threadIdx.x < 32) {
-        best = sb[threadIdx.x];
-        bi = si[threadIdx.x];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ob > best || (ob == best && oi < bi)) {
-                best = ob;
-                bi = oi;
-            }
-        }
-        if (threadIdx.x == 0) out[blockIdx.x] = (bi == 0x7fffffff) ? 0 : bi;  // all-NaN row -> 0
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) argmax_merge(best, bi, sb[w], si[w]);
+        pmax[row * AM_SPLIT + sp] = best;
+        pidx[row * AM_SPLIT + sp] = bi;
     }
 }
 
-int argmax(cudaStream_t stream, const float* logits, int B, int V, int64_t* out) {
+__global__ void __launch_bounds__(32)
+argmax_final_kernel(const float* __restrict__ pmax, const int* __restrict__ pidx, int64_t* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int row = blockIdx.x, lane = threadIdx.x;
+    float best = pmax[row * AM_SPLIT + lane];
+    int bi = pidx[row * AM_SPLIT + lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) argmax_merge(best, bi, __shfl_xor_sync(0xffffffffu, best, o), __shfl_xor_sync(0xffffffffu, bi, o));
+    if (lane == 0) out[row] = (bi == 0x7fffffff) ? 0 : bi;
+}
+
+size_t argmax_scratch_bytes(int B) { return static_cast<size_t>(B) * AM_SPLIT * (sizeof(float) + sizeof(int)); }
+
+int argmax(cudaStream_t stream, const float* logits, int B, int V, int64_t* out, void* scratch) {
     if (B <= 0) return 0;
-    argmax_kernel<<<B, 1024, 0, stream>>>(logits, V, out);
-    AF3_CHECK_LAUNCH();
+    AF3_REQUIRE(scratch != nullptr, "argmax: scratch of af3_argmax_scratch_bytes(B) bytes required");
+    float* pmax = static_cast<float*>(scratch);
+    int* pidx = reinterpret_cast<int*>(pmax + static_cast<size_t>(B) * AM_SPLIT);
+    AF3_CHECK_CUDA(launch_kernel(argmax_partial_kernel, dim3(B, AM_SPLIT), dim3(256), 0, stream, logits, V, pmax, pidx));
+    AF3_CHECK_CUDA(launch_kernel(argmax_final_kernel, dim3(B), dim3(32), 0, stream, static_cast<const float*>(pmax),
+                                 static_cast<const int*>(pidx), out));
     return 0;
 }
 

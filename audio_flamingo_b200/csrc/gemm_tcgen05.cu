@@ -130,6 +130,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();  // the next kernel may start its prologue / weight prefetch behind us
 
     const int k_splits = SWAP ? a.k_splits : 1;
     const int num_tiles = a.num_r_tiles * a.num_c_tiles * k_splits;  // work items: (tile, split), split fastest
@@ -141,18 +142,40 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            // Swap mode: the row operand is a WEIGHT matrix, independent of earlier kernels -> its first STAGES tiles are
+            // requested before pdl_wait(), so weight streaming overlaps the tail of the previous kernel(s).
+            int prefetched = 0;
+            if constexpr (SWAP) {
+                const int t0 = blockIdx.x;
+                if (t0 < num_tiles) {
+                    int r, c;
+                    tile_coords(t0 / k_splits, a, r, c);
+                    const int sp = t0 % k_splits;
+                    for (int kb = kb_lo(sp); kb < kb_lo(sp + 1) && prefetched < STAGES; ++kb, ++prefetched) {
+                        mbar_arrive_expect_tx(&full[prefetched], Cfg::STAGE_BYTES);
+                        uint8_t* sR = smem + prefetched * Cfg::STAGE_BYTES;
+#pragma unroll
+                        for (int na = 0; na < NA; ++na)
+                            tma_load_2d(sR + na * 128 * BK * 2, &map_r, &full[prefetched], kb * BK, (r * NA + na) * 128);
+                    }
+                }
+            }
+            pdl_wait();
+            int issued = 0;  // k-blocks issued so far by this CTA (the first `prefetched` already have their weights in flight)
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
                 int r, c;
                 tile_coords(t / k_splits, a, r, c);
                 const int sp = t % k_splits;
-                for (int kb = kb_lo(sp); kb < kb_lo(sp + 1); ++kb) {
-                    mbar_wait(&empty[stage], phase ^ 1);
+                for (int kb = kb_lo(sp); kb < kb_lo(sp + 1); ++kb, ++issued) {
                     uint8_t* sR = smem + stage * Cfg::STAGE_BYTES;
                     uint8_t* sC = sR + Cfg::R_BYTES;
-                    mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+                    if (issued >= prefetched) {
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
 #pragma unroll
-                    for (int na = 0; na < NA; ++na)
-                        tma_load_2d(sR + na * 128 * BK * 2, &map_r, &full[stage], kb * BK, (r * NA + na) * 128);
+                        for (int na = 0; na < NA; ++na)
+                            tma_load_2d(sR + na * 128 * BK * 2, &map_r, &full[stage], kb * BK, (r * NA + na) * 128);
+                    }
                     tma_load_2d(sC, &map_c, &full[stage], kb * BK, c * BN);
                     if (++stage == STAGES) {
                         stage = 0;
@@ -207,6 +230,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
         const int q = warp & 3;  // TMEM lane quarter this warp may access
         const int row_in_tile = q * 32 + lane;
         const int flags = (EPI >= 0) ? EPI : a.flags;
+        pdl_wait();  // residual reads / output writes / split-K workspace are ordered after every earlier kernel
         int acc = 0;
         uint32_t acc_phase = 0;
         uint32_t egrp = 0;             // running 64-column group counter of this warp (selects the staging buffer)
@@ -528,8 +552,7 @@ static int launch_epi(const CUtensorMap& mr, const CUtensorMap& mc, const CUtens
     }
     const int tiles = a.num_r_tiles * a.num_c_tiles * (SWAP && a.k_splits > 1 ? a.k_splits : 1);
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    kern<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(mr, mc, mo, mres, a);
-    AF3_CHECK_LAUNCH();
+    AF3_CHECK_CUDA(launch_kernel(kern, dim3(grid), dim3(192), Cfg::SMEM_BYTES, stream, mr, mc, mo, mres, a));
     return 0;
 }
 

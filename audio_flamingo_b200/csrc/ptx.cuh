@@ -56,6 +56,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// Both are no-ops for a grid launched without programmatic dependencies.
+//   pdl_launch_dependents: lets the next kernel in the stream start its prologue (and prefetch data that does not depend
+//                          on this kernel, e.g. weights) while this grid is still running.
+//   pdl_wait             : blocks until every prerequisite grid has completed and its memory is visible; must precede
+//                          the first access to data produced by earlier kernels and the first global write.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- proxy fences
 // generic-proxy smem writes -> visible to the async proxy (UMMA / TMA reads of smem)
 __device__ __forceinline__ void fence_proxy_async_smem() {

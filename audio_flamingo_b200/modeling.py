@@ -16,13 +16,14 @@ reference with model.to(torch.bfloat16).
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import Optional
 
 import torch
 from torch import nn
 
-from . import ops
+from . import _lib, ops
 from ._lib import AF3Error
 
 bf16 = torch.bfloat16
@@ -524,11 +525,10 @@ class AudioFlamingo3ForConditionalGeneration(nn.Module):
                     break
             if i + 1 == max_new_tokens:
                 break
-            logits = step_fn(next_ids)
+            logits, next_ids = step_fn(next_ids)   # one cached step incl. the greedy argmax (GEN:2793)
             cache.length += 1
             if return_logits:
                 kept_logits.append(logits.clone())
-            next_ids = ops.argmax(logits)
         result = out[:, : S + n_done]
         self._mark("decode_done")
         if return_logits:
@@ -536,21 +536,30 @@ class AudioFlamingo3ForConditionalGeneration(nn.Module):
         return result
 
     def _decode_runner(self, B, cache, use_graph):
-        """Returns step(next_ids[int64 B]) -> fp32 logits [B, V].  With use_graph the whole step (embedding gather, 28
-        layers, head) is captured once in a CUDA graph and replayed; positions advance on the device."""
+        """Returns step(next_ids[int64 B]) -> (fp32 logits [B, V], greedy ids [B]).  With use_graph the whole step (embedding
+        gather, 28 layers, head, argmax) is captured once in a CUDA graph and replayed; positions advance on the device."""
         lm = self.language_model
         dev = lm.lm_head.weight.device
         table = lm.model.embed_tokens.weight
         scratch = ops.decode_attention_scratch(B, lm.H, lm.D, cache.Tmax, dev)
         ids_buf = torch.zeros((B,), device=dev, dtype=torch.int64)
 
+        use_pdl = os.environ.get("AF3_PDL", "1") != "0"
+
         def eager(next_ids):
-            x, _ = ops.embed_scatter(next_ids, table, -1, None, 0, 1, None)
-            return lm.decode_step(x, cache, scratch)
+            # programmatic dependent launch along the whole step: each kernel's prologue and the GEMMs' weight
+            # prefetch overlap the tail of the kernel before it (the kernels order their dependent accesses themselves)
+            _lib.load().af3_set_pdl(1 if use_pdl else 0)
+            try:
+                x, _ = ops.embed_scatter(next_ids, table, -1, None, 0, 1, None)
+                logits = lm.decode_step(x, cache, scratch)
+                return logits, ops.argmax(logits)
+            finally:
+                _lib.load().af3_set_pdl(0)
 
         if not use_graph:
             return eager
-        state = {"graph": None, "logits": None, "warm": 0}
+        state = {"graph": None, "out": None, "warm": 0}
 
         def step(next_ids):
             ids_buf.copy_(next_ids)
@@ -563,13 +572,13 @@ class AudioFlamingo3ForConditionalGeneration(nn.Module):
                 prof, ops.PROFILE = ops.PROFILE, None  # timing events cannot be recorded inside a capture
                 n0 = ops.LAUNCHES
                 with torch.cuda.graph(g):
-                    state["logits"] = eager(ids_buf)
+                    state["out"] = eager(ids_buf)
                 state["launches"] = ops.LAUNCHES - n0
                 ops.LAUNCHES = n0  # capture launched nothing; replays are counted below
                 ops.PROFILE = prof
                 state["graph"] = g
             state["graph"].replay()  # (capture does not execute: the first replay runs this token's step)
             ops._count(state["launches"])
-            return state["logits"]
+            return state["out"]
 
         return step

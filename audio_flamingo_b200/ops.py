@@ -200,7 +200,8 @@ def layernorm(x, gamma, beta, eps=1e-5, out=None):
     rows, dim = x.shape
     if out is None:
         out = torch.empty_like(x)
-    check(lib.af3_layernorm(stream_ptr(), ptr(x), ptr(out), ptr(gamma), ptr(beta), rows, dim, eps), "af3_layernorm")
+    with _Timed(("layernorm", rows, dim, 0, 0)):
+        check(lib.af3_layernorm(stream_ptr(), ptr(x), ptr(out), ptr(gamma), ptr(beta), rows, dim, eps), "af3_layernorm")
     _count(1)
     return out
 
@@ -210,7 +211,8 @@ def avgpool_layernorm(x, n_win, T, gamma, beta, eps=1e-5):
     _req(x, bf16, "x")
     dim = x.shape[1]
     out = torch.empty((n_win * (T // 2), dim), device=x.device, dtype=bf16)
-    check(lib.af3_avgpool_layernorm(stream_ptr(), ptr(x), ptr(out), ptr(gamma), ptr(beta), n_win, T, dim, eps), "af3_avgpool_layernorm")
+    with _Timed(("layernorm", n_win * (T // 2), dim, 0, 1)):
+        check(lib.af3_avgpool_layernorm(stream_ptr(), ptr(x), ptr(out), ptr(gamma), ptr(beta), n_win, T, dim, eps), "af3_avgpool_layernorm")
     _count(1)
     return out
 
@@ -222,7 +224,8 @@ def rmsnorm(x, weight, eps=1e-6, row_idx=None, out=None):
     rows = x.shape[0] if row_idx is None else row_idx.numel()
     if out is None:
         out = torch.empty((rows, dim), device=x.device, dtype=bf16)
-    check(lib.af3_rmsnorm(stream_ptr(), ptr(x), ptr(out), ptr(weight), rows, dim, eps, ptr(row_idx)), "af3_rmsnorm")
+    with _Timed(("rmsnorm", rows, dim, 0, 0)):
+        check(lib.af3_rmsnorm(stream_ptr(), ptr(x), ptr(out), ptr(weight), rows, dim, eps, ptr(row_idx)), "af3_rmsnorm")
     _count(1)
     return out
 
@@ -244,22 +247,24 @@ def attention(q, k, v, out, *, B, H, Hkv, D, Tq, Tk, scale, causal, kv_layout=0,
 def rope_kv_append(qkv, k_cache, v_cache, *, B, T, H, Hkv, D, pos0, inv_freq, kv_start=None, pos0_dev=None):
     lib = _lib.load()
     Tmax = k_cache.shape[2]
-    check(
-        lib.af3_rope_kv_append(stream_ptr(), ptr(qkv), ptr(k_cache), ptr(v_cache), B, T, H, Hkv, D, Tmax, pos0, ptr(pos0_dev),
-                               ptr(kv_start), ptr(inv_freq)),
-        "af3_rope_kv_append",
-    )
+    with _Timed(("rope", B * T, H + 2 * Hkv, D, 0)):
+        check(
+            lib.af3_rope_kv_append(stream_ptr(), ptr(qkv), ptr(k_cache), ptr(v_cache), B, T, H, Hkv, D, Tmax, pos0, ptr(pos0_dev),
+                                   ptr(kv_start), ptr(inv_freq)),
+            "af3_rope_kv_append",
+        )
     _count(1)
 
 
 def decode_attention(qkv, k_cache, v_cache, out, scratch, *, B, H, Hkv, D, ctx_len, kv_start, scale):
     lib = _lib.load()
     Tmax = k_cache.shape[2]
-    check(
-        lib.af3_decode_attention(stream_ptr(), ptr(qkv), ptr(k_cache), ptr(v_cache), ptr(out), ptr(scratch), B, H, Hkv, D,
-                                 Tmax, ptr(ctx_len), ptr(kv_start), float(scale)),
-        "af3_decode_attention",
-    )
+    with _Timed(("decode_attention", B, H, Tmax, 0)):
+        check(
+            lib.af3_decode_attention(stream_ptr(), ptr(qkv), ptr(k_cache), ptr(v_cache), ptr(out), ptr(scratch), B, H, Hkv, D,
+                                     Tmax, ptr(ctx_len), ptr(kv_start), float(scale)),
+            "af3_decode_attention",
+        )
     _count(2)
     return out
 
@@ -284,11 +289,12 @@ def embed_scatter(ids, table, audio_token_id, audio_embeds, n_win, frames, post_
         audio_embeds = table  # never read: n_win = 0 -> no valid rows
         n_win, frames = 0, 1
         post_len = counts
-    check(
-        lib.af3_embed_scatter(stream_ptr(), ptr(ids), n_tok, ptr(table), dim, int(audio_token_id), ptr(audio_embeds), n_win,
-                              frames, ptr(post_len), ptr(out), ptr(scratch), ptr(counts)),
-        "af3_embed_scatter",
-    )
+    with _Timed(("embed_scatter", n_tok, dim, 0, 0)):
+        check(
+            lib.af3_embed_scatter(stream_ptr(), ptr(ids), n_tok, ptr(table), dim, int(audio_token_id), ptr(audio_embeds), n_win,
+                                  frames, ptr(post_len), ptr(out), ptr(scratch), ptr(counts)),
+            "af3_embed_scatter",
+        )
     _count(2)
     return out, counts
 
@@ -299,6 +305,8 @@ def argmax(logits, out=None):
     B, V = logits.shape
     if out is None:
         out = torch.empty((B,), device=logits.device, dtype=torch.int64)
-    check(lib.af3_argmax(stream_ptr(), ptr(logits), B, V, ptr(out)), "af3_argmax")
-    _count(1)
+    scratch = torch.empty((lib.af3_argmax_scratch_bytes(B),), device=logits.device, dtype=torch.uint8)
+    with _Timed(("argmax", B, V, 0, 0)):
+        check(lib.af3_argmax(stream_ptr(), ptr(logits), B, V, ptr(out), ptr(scratch)), "af3_argmax")
+    _count(2)
     return out

@@ -223,11 +223,18 @@ def run_ours(args):
     step(True)  # warm the host path (pinned staging, H2D)
     ms_e2e, _, _ = timed(args.steps, from_host=True)
 
-    # one profiled step (per-kernel CUDA events around every GEMM / attention / log-mel launch)
+    # one profiled step (per-kernel CUDA events around every launch; PDL off so kernels do not overlap their brackets;
+    # the decode steps replayed from the CUDA graph are not bracketed, the first -- eager -- decode step is)
     ops.PROFILE = {}
+    pdl_env = os.environ.get("AF3_PDL")
+    os.environ["AF3_PDL"] = "0"
     torch.cuda.synchronize()
     step(False)
     torch.cuda.synchronize()
+    if pdl_env is None:
+        os.environ.pop("AF3_PDL")
+    else:
+        os.environ["AF3_PDL"] = pdl_env
     prof, ops.PROFILE = ops.PROFILE, None
 
     if rank != 0:
@@ -273,7 +280,19 @@ def run_ours(args):
             bytes_alg = a * (b * 4 + 128 * (b // 160) * 4)
             table.append({"kernel": "logmel", "n_win": a, "launches": len(evs), "ms_total": tot, "gbs": bytes_alg * len(evs) / (tot * 1e-3) / 1e9,
                           "bytes_per_launch": bytes_alg})
+        else:
+            table.append({"kernel": kind, "shape": [a, b, c, flags], "launches": len(evs), "ms_total": tot})
     table.sort(key=lambda r: -r["ms_total"])
+    # eager decode step breakdown (ms per step by kernel kind; rows with 32 tokens)
+    dec = {}
+    for r in table:
+        if r["kernel"] == "gemm_tcgen05" and r["n_tok"] == B:
+            name = f"gemm {r['n_feat']}x{r['K']}"
+        elif r["kernel"] in ("rmsnorm", "rope", "decode_attention", "embed_scatter", "argmax") and r["shape"][0] in (B, 1):
+            name = r["kernel"]
+        else:
+            continue
+        dec[name] = dec.get(name, 0.0) + r["ms_total"]
     top = next((r for r in table if r["kernel"] == "gemm_tcgen05"), None)
     ncu = {}
     ncu_file = ROOT / "profiles" / "ncu_summary.json"
@@ -323,7 +342,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(tokens_host.numel() * 8), "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
         "audio_s_per_s": audio_s_per_s, "decode_tok_s": decode_tok_s, "stage_ms": stage_ms,
-        "roofline": roofline, "roofline_decode_step": decode_roofline, "kernels": table[:12],
+        "roofline": roofline, "roofline_decode_step": decode_roofline, "kernels": table[:14], "decode_step_kernel_ms": dec,
         "cpu_baseline": cpu, "clocks": clocks,
     }
     print(json.dumps(line))

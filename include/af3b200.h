@@ -23,6 +23,11 @@ extern "C" {
 const char* af3_last_error(void);
 int af3_abi_version(void);
 
+/* Programmatic dependent launch for subsequent launches of the decode-step kernels (GEMM, RMSNorm, RoPE, decode
+ * attention, embedding gather, argmax): the next kernel's prologue and weight prefetch overlap the previous kernel's
+ * tail; results are identical.  Process-wide switch, off by default. */
+void af3_set_pdl(int enable);
+
 /* ---- epilogue flags for af3_gemm_bf16 ---- */
 #define AF3_EPI_BIAS 1
 #define AF3_EPI_GELU 2
@@ -108,8 +113,10 @@ int af3_embed_scatter(void* stream, const int64_t* ids, int n_tok, const void* e
                       int64_t audio_token_id, const void* audio_embeds, int n_win, int frames, const int* post_len,
                       void* out, int* scratch_rows /*[n_tok]*/, int* counts /*[2]*/);
 
-/* Greedy step (GEN:2762-2800): argmax over fp32 logits [B, V] (first max index, like torch.argmax). */
-int af3_argmax(void* stream, const float* logits, int B, int V, int64_t* out_ids);
+/* Greedy step (GEN:2762-2800): argmax over fp32 logits [B, V] (first max index, like torch.argmax).
+ * scratch: af3_argmax_scratch_bytes(B) bytes of device memory (two-stage reduction). */
+size_t af3_argmax_scratch_bytes(int B);
+int af3_argmax(void* stream, const float* logits, int B, int V, int64_t* out_ids, void* scratch);
 
 #ifdef __cplusplus
 }

@@ -143,3 +143,22 @@ def test_multi_window_and_multi_audio_prompts(O):
     bad[0, -1] = aid
     with pytest.raises(ValueError):
         ours(input_ids=bad.cuda(), attention_mask=am.cuda(), input_features=fo["input_features"], input_features_mask=fo["input_features_mask"])
+
+
+def test_pdl_decode_is_bit_identical(O, monkeypatch):
+    """Programmatic dependent launch only reorders prologues / weight prefetch: ids and logits must not change."""
+    from audio_flamingo_b200 import AudioFlamingo3ForConditionalGeneration
+
+    ref32 = O.hf_model("mid", seed=4, sharpen=8.0)
+    cfg = ref32.config
+    waves, feats, fmask, ids, am = _inputs(O, cfg, [30.0, 9.0], seed=7)
+    ours = AudioFlamingo3ForConditionalGeneration.from_reference(ref32, device="cuda")
+    kw = dict(input_ids=ids.cuda(), attention_mask=am.cuda(), input_features=feats.cuda(), input_features_mask=fmask.cuda(),
+              max_new_tokens=10, return_logits=True)
+    monkeypatch.setenv("AF3_PDL", "1")
+    g1, l1 = ours.generate(**kw)
+    g1e, l1e = ours.generate(use_cuda_graph=False, **kw)
+    monkeypatch.setenv("AF3_PDL", "0")
+    g0, l0 = ours.generate(**kw)
+    assert torch.equal(g1, g0) and torch.equal(l1, l0)
+    assert torch.equal(g1e, g0) and torch.equal(l1e, l0)
