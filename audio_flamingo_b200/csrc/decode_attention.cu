@@ -1,27 +1,45 @@
 // Single-query (decode step) GQA attention over the pre-allocated KV cache; replaces SDPA at q_len = 1
 // ([O] Q2M:227-238 -> SDPA:40-104) and the torch.cat cache growth (CACHE:119-120: the cache here is written in
-// place by rope_kv_append).  HBM-bound: every K and V byte of the live context is read exactly once per step:
-// one CTA = one (sequence, KV head, 128-key chunk) and serves all G = H/Hkv query heads that share the KV head
-// (scores: one thread per key, 16-byte loads of its K row, q broadcast from shared memory; P.V: one thread per output
-// dim, coalesced V rows).  B*Hkv*ceil(Tmax/128) CTAs cover the GPU; a second kernel merges the chunk partials
-// (log-sum-exp combine).  ctx_len lives in device memory so the launch parameters are step-invariant (CUDA-graph
-// replay); chunks beyond the live context exit immediately.
+// place by rope_kv_append).  HBM-bound: every K and V byte of the live context is read exactly once per step.
+//
+// One CTA = one (sequence, KV head, 128-key chunk) and serves all G = H/Hkv (<= 16) query heads sharing the KV head.
+// The problem is transposed so that the 128 keys / 128 output dims are the UMMA M dimension and the (padded) 16 query
+// heads are N:
+//     S^T[key, head] = K_tile[key, :] . Q[head, :]          tcgen05.mma 128x16x16 x 8,  A = K tile (K-major, via TMA)
+//     O^T[dim, head] = V_tile^T[dim, key] . P^T[key, head]   tcgen05.mma 128x16x16 x 8,  A = V tile read MN-major
+// so the K and V tiles stream HBM -> smem by TMA (2 x 32 KB in flight per CTA, 3 CTAs/SM) and never pass through
+// registers; the softmax over the chunk is a cross-lane reduction of 16 columns (thread = key = TMEM lane).
+// B*Hkv*ceil(Tmax/128) CTAs cover the GPU; a second kernel merges the chunk partials (log-sum-exp combine).
+// ctx_len lives in device memory so the launch parameters are step-invariant (CUDA-graph replay); chunks beyond the
+// live context exit immediately.  Cache rows beyond the live context must hold finite values (the cache is
+// zero-initialised): they are multiplied by P = 0.
 // Algorithmic bytes per step: 2 (K,V) * Hkv * D * 2 B * ctx * B  (= 57344 B per token per sequence at 28 layers).
 #include "common.h"
 #include "ptx.cuh"
 
 namespace af3 {
 
-constexpr int DA_THREADS = 128;
-constexpr int DA_CHUNK = 128;   // keys per CTA (one per thread in the score phase)
-constexpr int DA_MAXG = 8;      // max query heads per KV head
+constexpr int DA_CHUNK = 128;    // keys per CTA
+constexpr int DA_NH = 16;        // query heads per KV head, padded (UMMA N)
+constexpr int DA_THREADS = 160;  // warps 0-3: softmax / epilogue (thread = TMEM lane), warp 4: TMA + MMA issue
+constexpr int DA_D = 128;
+constexpr int DA_SMEM = 2 * DA_CHUNK * DA_D * 2 /*K,V*/ + 2 * (DA_NH * 128) /*Q: 2 blocks of 16 x 128 B*/ +
+                        2 * (DA_NH * 128) /*P*/ + 1024 /*align*/ + 1024 /*barriers + reduction scratch*/;
 
-template <int D>
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+
 __global__ void __launch_bounds__(DA_THREADS)
-decode_attn_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ k_cache, const bf16* __restrict__ v_cache,
-                   float* __restrict__ part, int H, int Hkv, int Tmax, int nsplit, const int* __restrict__ ctx_len_p,
-                   const int* __restrict__ kv_start, float scale) {
-    static_assert(D == DA_THREADS, "one thread per output dim");
+decode_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                   const __grid_constant__ CUtensorMap map_v, float* __restrict__ part, int H, int Hkv, int nsplit,
+                   const int* __restrict__ ctx_len_p, const int* __restrict__ kv_start, float scale_log2) {
+    constexpr int D = DA_D;
     const int G = H / Hkv;
     const int b = blockIdx.x, hk = blockIdx.y, sp = blockIdx.z;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -33,142 +51,143 @@ decode_attn_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ k_cach
     const int j_beg = max(j0, start), j_end = min(j0 + DA_CHUNK, ctx);
     float* pbase = part + ((static_cast<size_t>(b) * H + hk * G) * nsplit + sp) * (D + 2);
     if (j_beg >= j_end) {  // chunk entirely outside the live context: publish an empty partial
-        for (int g = 0; g < G; ++g) {
-            float* dst = pbase + static_cast<size_t>(g) * nsplit * (D + 2);
-            if (tid == 0) {
-                dst[D] = -INFINITY;
-                dst[D + 1] = 0.f;
-            }
+        if (tid < G) {
+            float* dst = pbase + static_cast<size_t>(tid) * nsplit * (D + 2);
+            dst[D] = -INFINITY;
+            dst[D + 1] = 0.f;
         }
         return;
     }
-    __shared__ __align__(16) float q_s[DA_MAXG][D];
-    __shared__ float p_s[DA_MAXG][DA_CHUNK];
-    __shared__ float red_m[DA_MAXG][4], red_l[DA_MAXG][4];
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sK = smem;                   // 2 blocks [128 keys x 128 B]
+    uint8_t* sV = sK + DA_CHUNK * D * 2;  // 2 blocks [128 keys x 128 B]
+    uint8_t* sQ = sV + DA_CHUNK * D * 2;  // 2 blocks [16 heads x 128 B]
+    uint8_t* sP = sQ + 2 * DA_NH * 128;   // 2 blocks [16 heads x 128 B]  (64 keys along each 128-byte row)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * DA_NH * 128);
+    uint64_t *qk_full = bars, *v_full = bars + 1, *s_full = bars + 2, *p_full = bars + 3, *o_full = bars + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+    float* red = reinterpret_cast<float*>(bars + 6);  // [2][4 warps][16 heads]
 
-    const bf16* qrow = qkv + static_cast<size_t>(b) * (H + 2 * Hkv) * D + static_cast<size_t>(hk) * G * D;
-    for (int i = tid; i < G * D; i += DA_THREADS) q_s[i / D][i % D] = __bfloat162float(qrow[i]) * scale;
+    if (tid == 128) {
+        tma_prefetch_desc(&map_q);
+        tma_prefetch_desc(&map_k);
+        tma_prefetch_desc(&map_v);
+        mbar_init(qk_full, 1);
+        mbar_init(v_full, 1);
+        mbar_init(s_full, 1);
+        mbar_init(p_full, 128);
+        mbar_init(o_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) {
+        tmem_alloc(tmem_slot, 32);
+        tmem_relinquish();
+    }
+    tc_fence_before();
     __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_S = *tmem_slot, tmem_O = tmem_S + DA_NH;
 
-    // ---- scores: thread = key
-    const int j = j0 + tid;
-    const bool valid = j >= j_beg && j < j_end;
-    float s[DA_MAXG];
+    if (warp == 4) {
+        if (lane == 0) {
+            // all three operands in flight at once
+            mbar_arrive_expect_tx(qk_full, DA_CHUNK * D * 2 + 2 * DA_NH * 128);
 #pragma unroll
-    for (int g = 0; g < DA_MAXG; ++g) s[g] = 0.f;
-    if (valid) {
-        const uint4* kp = reinterpret_cast<const uint4*>(k_cache + ((static_cast<size_t>(b) * Hkv + hk) * Tmax + j) * D);
-        uint4 kreg[D / 8];
-#pragma unroll
-        for (int c = 0; c < D / 8; ++c) kreg[c] = __ldg(kp + c);  // the whole 256-byte K row in flight at once
-#pragma unroll
-        for (int c = 0; c < D / 8; ++c) {
-            const uint4 kv = kreg[c];
-            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&kv);
-            float kf[8];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float2 t = __bfloat1622float2(h2[e]);
-                kf[2 * e] = t.x;
-                kf[2 * e + 1] = t.y;
+            for (int db = 0; db < 2; ++db) {
+                tma_load_2d(sQ + db * DA_NH * 128, &map_q, qk_full, db * 64, b * (H + 2 * Hkv) + hk * G);
+                tma_load_3d(sK + db * 16384, &map_k, qk_full, db * 64, j0, b * Hkv + hk);
             }
+            mbar_arrive_expect_tx(v_full, DA_CHUNK * D * 2);
 #pragma unroll
-            for (int g = 0; g < DA_MAXG; ++g) {
-                if (g < G) {
-                    const float4 qa = *reinterpret_cast<const float4*>(&q_s[g][c * 8]);
-                    const float4 qb = *reinterpret_cast<const float4*>(&q_s[g][c * 8 + 4]);
-                    s[g] += kf[0] * qa.x + kf[1] * qa.y + kf[2] * qa.z + kf[3] * qa.w + kf[4] * qb.x + kf[5] * qb.y +
-                            kf[6] * qb.z + kf[7] * qb.w;
+            for (int db = 0; db < 2; ++db) tma_load_3d(sV + db * 16384, &map_v, v_full, db * 64, j0, b * Hkv + hk);
+            constexpr uint32_t idesc_s = make_idesc_bf16(128, DA_NH, 0, 0);
+            constexpr uint32_t idesc_o = make_idesc_bf16(128, DA_NH, 1, 0);  // A (= V tile) is MN-major
+            const uint32_t aK = smem_u32(sK), aQ = smem_u32(sQ), aV = smem_u32(sV), aP = smem_u32(sP);
+            // S^T = K . Q^T
+            mbar_wait(qk_full, 0);
+            tc_fence_after();
+#pragma unroll
+            for (int kk = 0; kk < D / 16; ++kk)
+                umma_bf16_ss(tmem_S, make_smem_desc_sw128(aK + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024),
+                             make_smem_desc_sw128(aQ + (kk >> 2) * (DA_NH * 128) + (kk & 3) * 32, 0, 1024), idesc_s, kk != 0);
+            umma_commit(s_full);
+            // O^T = V^T . P^T
+            mbar_wait(p_full, 0);
+            mbar_wait(v_full, 0);
+            tc_fence_after();
+#pragma unroll
+            for (int kk = 0; kk < DA_CHUNK / 16; ++kk)
+                umma_bf16_ss(tmem_O, make_smem_desc_sw128(aV + kk * 2048, 16384, 1024),
+                             make_smem_desc_sw128(aP + (kk >> 2) * (DA_NH * 128) + (kk & 3) * 32, 0, 1024), idesc_o, kk != 0);
+            umma_commit(o_full);
+        }
+        __syncwarp();
+    } else {
+        // ---- softmax over the chunk: thread = key (TMEM lane), 16 columns = heads
+        const int j = j0 + tid;
+        const bool valid = j >= j_beg && j < j_end;
+        const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+        mbar_wait(s_full, 0);
+        tc_fence_after();
+        uint32_t sv[16];
+        tmem_ld16(tmem_S + lane_off, sv);
+        tmem_ld_wait();
+        float t[DA_NH], m[DA_NH], p[DA_NH];
+#pragma unroll
+        for (int g = 0; g < DA_NH; ++g) {
+            t[g] = (valid && g < G) ? __uint_as_float(sv[g]) * scale_log2 : -INFINITY;
+            float mx = t[g];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            if (lane == 0) red[warp * DA_NH + g] = mx;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+        for (int g = 0; g < DA_NH; ++g) {
+            m[g] = fmaxf(fmaxf(red[g], red[DA_NH + g]), fmaxf(red[2 * DA_NH + g], red[3 * DA_NH + g]));
+            p[g] = (t[g] == -INFINITY) ? 0.f : exp2f(t[g] - m[g]);
+            float ps = p[g];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
+            if (lane == 0) red[64 + warp * DA_NH + g] = ps;
+        }
+        // P^T[key = tid][head g] -> B tile [16 heads][128 keys], K-major, 128B swizzle: row g, key column tid
+        {
+            uint8_t* blk = sP + (tid >> 6) * (DA_NH * 128);
+            const int kc = tid & 63;
+#pragma unroll
+            for (int g = 0; g < DA_NH; ++g)
+                *reinterpret_cast<bf16*>(blk + g * 128 + ((((kc >> 3) ^ (g & 7)) << 4) | ((kc & 7) << 1))) = __float2bfloat16_rn(p[g]);
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(p_full);
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // red[64..] complete
+        // ---- O^T[dim = tid][head] -> partial
+        mbar_wait(o_full, 0);
+        tc_fence_after();
+        uint32_t ov[16];
+        tmem_ld16(tmem_O + lane_off, ov);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < DA_NH; ++g) {
+            if (g < G) {
+                float* dst = pbase + static_cast<size_t>(g) * nsplit * (D + 2);
+                dst[tid] = __uint_as_float(ov[g]);
+                if (tid == 0) {
+                    dst[D] = m[g];
+                    dst[D + 1] = red[64 + g] + red[64 + DA_NH + g] + red[64 + 2 * DA_NH + g] + red[64 + 3 * DA_NH + g];
                 }
             }
         }
     }
-    // ---- chunk softmax statistics per head
-#pragma unroll
-    for (int g = 0; g < DA_MAXG; ++g) {
-        float mx = valid ? s[g] : -INFINITY;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        if (lane == 0) red_m[g][warp] = mx;
-    }
+    tc_fence_before();
     __syncthreads();
-    float m_c[DA_MAXG];
-#pragma unroll
-    for (int g = 0; g < DA_MAXG; ++g) {
-        m_c[g] = fmaxf(fmaxf(red_m[g][0], red_m[g][1]), fmaxf(red_m[g][2], red_m[g][3]));
-        const float p = valid ? __expf(s[g] - m_c[g]) : 0.f;
-        p_s[g][tid] = bf16_round(p);  // P is rounded to bf16 before P.V as in flash-style SDPA kernels
-        float ps = p;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
-        if (lane == 0) red_l[g][warp] = ps;
-    }
-    __syncthreads();
-    // ---- P.V: warp w takes keys jj = w, w+4, ...; lane owns dims 4*lane .. 4*lane+3 (8-byte loads, a warp reads a whole
-    //      256-byte V row); 8 independent row loads in flight per warp; cross-warp reduction through shared memory
-    float o_acc[DA_MAXG][4];
-#pragma unroll
-    for (int g = 0; g < DA_MAXG; ++g)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) o_acc[g][e] = 0.f;
-    const bf16* vbase = v_cache + ((static_cast<size_t>(b) * Hkv + hk) * Tmax + j0) * D + lane * 4;
-    const int jj0 = j_beg - j0, jj1 = j_end - j0;
-    for (int jb = jj0 + warp; jb < jj1; jb += 4 * 8) {
-        uint2 vv[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int jj = jb + 4 * u;
-            vv[u] = (jj < jj1) ? __ldg(reinterpret_cast<const uint2*>(vbase + static_cast<size_t>(jj) * D)) : make_uint2(0u, 0u);
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int jj = jb + 4 * u;
-            if (jj < jj1) {
-                const float2 va = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&vv[u].x));
-                const float2 vb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&vv[u].y));
-#pragma unroll
-                for (int g = 0; g < DA_MAXG; ++g) {
-                    if (g < G) {
-                        const float p = p_s[g][jj];
-                        o_acc[g][0] = fmaf(p, va.x, o_acc[g][0]);
-                        o_acc[g][1] = fmaf(p, va.y, o_acc[g][1]);
-                        o_acc[g][2] = fmaf(p, vb.x, o_acc[g][2]);
-                        o_acc[g][3] = fmaf(p, vb.y, o_acc[g][3]);
-                    }
-                }
-            }
-        }
-    }
-    __syncthreads();  // q_s is dead from here: reuse it as the cross-warp reduction buffer [warp][G*D] (G*D <= 1024 floats)
-    float* red = &q_s[0][0];
-    // four passes (one per warp) keep the buffer at G*D floats: warp w adds its partial in turn
-    for (int w = 0; w < 4; ++w) {
-        if (warp == w) {
-#pragma unroll
-            for (int g = 0; g < DA_MAXG; ++g) {
-                if (g < G) {
-                    float4* dst = reinterpret_cast<float4*>(red + g * D + lane * 4);
-                    float4 cur = (w == 0) ? make_float4(0.f, 0.f, 0.f, 0.f) : *dst;
-                    cur.x += o_acc[g][0];
-                    cur.y += o_acc[g][1];
-                    cur.z += o_acc[g][2];
-                    cur.w += o_acc[g][3];
-                    *dst = cur;
-                }
-            }
-        }
-        __syncthreads();
-    }
-    for (int g = 0; g < G; ++g) {
-        float* dst = pbase + static_cast<size_t>(g) * nsplit * (D + 2);
-        dst[tid] = red[g * D + tid];
-        if (tid == 0) {
-            dst[D] = m_c[g];
-            dst[D + 1] = red_l[g][0] + red_l[g][1] + red_l[g][2] + red_l[g][3];
-        }
-    }
+    if (warp == 0) tmem_dealloc(tmem_S, 32);
 }
 
+// partial layout: [b][h][split][D + 2] = (unnormalised o[D] relative to the chunk max, chunk max (log2 domain), chunk sum)
 template <int D>
 __global__ void __launch_bounds__(D)
 decode_attn_combine(const float* __restrict__ part, bf16* __restrict__ out, int H, int nsplit) {
@@ -182,7 +201,7 @@ decode_attn_combine(const float* __restrict__ part, bf16* __restrict__ out, int 
     for (int s = 0; s < nsplit; ++s) {
         const float ms = src[s * (D + 2) + D];
         if (ms == -INFINITY) continue;  // empty chunk (its o slots were never written)
-        const float w = __expf(ms - m);
+        const float w = exp2f(ms - m);
         l += w * src[s * (D + 2) + D + 1];
         o += w * src[s * (D + 2) + tid];
     }
@@ -199,13 +218,27 @@ int decode_attention(cudaStream_t stream, const bf16* qkv, const bf16* k_cache, 
                      float* scratch, int B, int H, int Hkv, int D, int Tmax, const int* ctx_len, const int* kv_start,
                      float scale) {
     AF3_REQUIRE(D == 128, "decode_attention: head_dim must be 128");
-    AF3_REQUIRE(H % Hkv == 0 && H / Hkv <= DA_MAXG, "decode_attention: at most 8 query heads per KV head");
+    AF3_REQUIRE(H % Hkv == 0 && H / Hkv <= DA_NH, "decode_attention: at most 16 query heads per KV head");
     AF3_REQUIRE(ctx_len != nullptr, "decode_attention: ctx_len must be a device pointer");
     const int ns = n_splits(Tmax);
     AF3_REQUIRE(ns <= 65535, "decode_attention: context too long");
+    static bool configured = false;
+    if (!configured) {
+        AF3_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DA_SMEM));
+        configured = true;
+    }
+    CUtensorMap mq, mk, mv;
+    // q heads as rows of 128: the packed projection row of sequence b holds (H + 2 Hkv) such rows
+    if (int e = make_tmap_2d(&mq, qkv, D, static_cast<uint64_t>(B) * (H + 2 * Hkv), D, 64, DA_NH)) return e;
+    if (int e = make_tmap_3d(&mk, k_cache, D, Tmax, static_cast<uint64_t>(B) * Hkv, D, static_cast<uint64_t>(Tmax) * D, 64,
+                             DA_CHUNK, 1))
+        return e;
+    if (int e = make_tmap_3d(&mv, v_cache, D, Tmax, static_cast<uint64_t>(B) * Hkv, D, static_cast<uint64_t>(Tmax) * D, 64,
+                             DA_CHUNK, 1))
+        return e;
     dim3 grid(B, Hkv, ns);
-    AF3_CHECK_CUDA(launch_kernel(decode_attn_kernel<128>, grid, dim3(DA_THREADS), 0, stream, qkv, k_cache, v_cache, scratch, H,
-                                 Hkv, Tmax, ns, ctx_len, kv_start, scale));
+    AF3_CHECK_CUDA(launch_kernel(decode_attn_kernel, grid, dim3(DA_THREADS), DA_SMEM, stream, mq, mk, mv, scratch, H, Hkv, ns,
+                                 ctx_len, kv_start, scale * 1.4426950408889634f));
     dim3 g2(B, H);
     AF3_CHECK_CUDA(launch_kernel(decode_attn_combine<128>, g2, dim3(128), 0, stream, static_cast<const float*>(scratch), out, H, ns));
     return 0;

@@ -224,8 +224,9 @@ class AF3KVCache:
     `length` = number of filled slots (host int); `pos_dev`/`ctx_dev` mirror it on the device for graph replay."""
 
     def __init__(self, n_layers, B, Hkv, Tmax, D, device):
-        self.k = torch.empty((n_layers, B, Hkv, Tmax, D), device=device, dtype=bf16)
-        self.v = torch.empty_like(self.k)
+        # zero-initialised: the decode attention kernel multiplies not-yet-written rows by P = 0 on the tensor cores
+        self.k = torch.zeros((n_layers, B, Hkv, Tmax, D), device=device, dtype=bf16)
+        self.v = torch.zeros_like(self.k)
         self.B, self.Tmax = B, Tmax
         self.length = 0
         self.kv_start = None  # int32 [B]: left-padding length per sequence
