@@ -30,7 +30,7 @@ constexpr int NORM_MAXV = 16;  // uint4 chunks per lane -> dim <= 4096
 // ---------------------------------------------------------------------------------------------------------
 // LayerNorm ([O] AF3M:224,232,366: nn.LayerNorm, eps 1e-5; fp32 statistics, one rounding to bf16).
 // POOL: the row is first formed as bf16((x[2t] + x[2t+1]) / 2)  (nn.AvgPool1d(2,2), AF3M:364-365).
-template <bool POOL>
+template <bool POOL, int NV>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const bf16* __restrict__ gamma,
                  const bf16* __restrict__ beta, int rows, int dim, float eps, int T_in, int T_out) {
@@ -38,7 +38,7 @@ layernorm_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const bf16* _
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
     const int nchunk = dim >> 3;
-    float v[NORM_MAXV][8];
+    float v[NV][8];
     float sum = 0.f;
     size_t in_row = row;
     if (POOL) {
@@ -47,7 +47,7 @@ layernorm_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const bf16* _
     }
     const uint4* xp = reinterpret_cast<const uint4*>(x + in_row * dim);
 #pragma unroll
-    for (int i = 0; i < NORM_MAXV; ++i) {
+    for (int i = 0; i < NV; ++i) {
         const int c = lane + 32 * i;
         if (c < nchunk) {
             unpack8(xp[c], v[i]);
@@ -64,7 +64,7 @@ layernorm_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const bf16* _
     const float mean = warp_sum(sum) / dim;
     float sq = 0.f;
 #pragma unroll
-    for (int i = 0; i < NORM_MAXV; ++i) {
+    for (int i = 0; i < NV; ++i) {
         const int c = lane + 32 * i;
         if (c < nchunk) {
 #pragma unroll
@@ -79,7 +79,7 @@ layernorm_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const bf16* _
     const uint4* gp = reinterpret_cast<const uint4*>(gamma);
     const uint4* bp = reinterpret_cast<const uint4*>(beta);
 #pragma unroll
-    for (int i = 0; i < NORM_MAXV; ++i) {
+    for (int i = 0; i < NV; ++i) {
         const int c = lane + 32 * i;
         if (c < nchunk) {
             float g[8], b[8], o[8];
@@ -92,13 +92,31 @@ layernorm_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const bf16* _
     }
 }
 
+// NV = 16-byte chunks per lane: sized to the row so the row lives in few registers (occupancy = bandwidth here)
+template <bool POOL>
+static int launch_layernorm(cudaStream_t stream, const bf16* x, bf16* y, const bf16* gamma, const bf16* beta, int rows, int dim,
+                            float eps, int T_in, int T_out) {
+    const int need = ceil_div(dim >> 3, 32);
+    dim3 grid(ceil_div(rows, 8)), block(256);
+#define AF3_LN_CASE(NV)                                                                                              \
+    if (need <= NV) {                                                                                                \
+        layernorm_kernel<POOL, NV><<<grid, block, 0, stream>>>(x, y, gamma, beta, rows, dim, eps, T_in, T_out);      \
+        AF3_CHECK_LAUNCH();                                                                                          \
+        return 0;                                                                                                    \
+    }
+    AF3_LN_CASE(2)
+    AF3_LN_CASE(5)
+    AF3_LN_CASE(8)
+    AF3_LN_CASE(16)
+#undef AF3_LN_CASE
+    return fail("layernorm: dim too large");
+}
+
 int layernorm(cudaStream_t stream, const bf16* x, bf16* y, const bf16* gamma, const bf16* beta, int rows, int dim,
               float eps) {
     AF3_REQUIRE(dim % 8 == 0 && dim <= NORM_MAXV * 256, "layernorm: dim must be a multiple of 8 and <= 4096");
     if (rows <= 0) return 0;
-    layernorm_kernel<false><<<ceil_div(rows, 8), 256, 0, stream>>>(x, y, gamma, beta, rows, dim, eps, 0, 0);
-    AF3_CHECK_LAUNCH();
-    return 0;
+    return launch_layernorm<false>(stream, x, y, gamma, beta, rows, dim, eps, 0, 0);
 }
 int avgpool_layernorm(cudaStream_t stream, const bf16* x, bf16* y, const bf16* gamma, const bf16* beta, int n_win,
                       int T, int dim, float eps) {
@@ -106,13 +124,12 @@ int avgpool_layernorm(cudaStream_t stream, const bf16* x, bf16* y, const bf16* g
     const int T_out = T / 2;
     const int rows = n_win * T_out;
     if (rows <= 0) return 0;
-    layernorm_kernel<true><<<ceil_div(rows, 8), 256, 0, stream>>>(x, y, gamma, beta, rows, dim, eps, T, T_out);
-    AF3_CHECK_LAUNCH();
-    return 0;
+    return launch_layernorm<true>(stream, x, y, gamma, beta, rows, dim, eps, T, T_out);
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // Qwen2RMSNorm ([O] Q2M:258-263): h = x.float(); h = h * rsqrt(mean(h^2) + eps); return weight * h.to(bf16).
+template <int NV>
 __global__ void __launch_bounds__(256)
 rmsnorm_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const bf16* __restrict__ weight, int rows, int dim,
                float eps, const int* __restrict__ row_idx) {
@@ -124,10 +141,10 @@ rmsnorm_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const bf16* __r
     const size_t in_row = row_idx ? static_cast<size_t>(row_idx[row]) : static_cast<size_t>(row);
     const int nchunk = dim >> 3;
     const uint4* xp = reinterpret_cast<const uint4*>(x + in_row * dim);
-    float v[NORM_MAXV][8];
+    float v[NV][8];
     float sq = 0.f;
 #pragma unroll
-    for (int i = 0; i < NORM_MAXV; ++i) {
+    for (int i = 0; i < NV; ++i) {
         const int c = lane + 32 * i;
         if (c < nchunk) {
             unpack8(xp[c], v[i]);
@@ -139,7 +156,7 @@ rmsnorm_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const bf16* __r
     uint4* yp = reinterpret_cast<uint4*>(y + static_cast<size_t>(row) * dim);
     const uint4* wp = reinterpret_cast<const uint4*>(weight);
 #pragma unroll
-    for (int i = 0; i < NORM_MAXV; ++i) {
+    for (int i = 0; i < NV; ++i) {
         const int c = lane + 32 * i;
         if (c < nchunk) {
             float w[8], o[8];
@@ -151,12 +168,67 @@ rmsnorm_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const bf16* __r
     }
 }
 
+// Few rows (decode step: 32 tokens): one CTA of 256 threads per row, so a 7 KB row is a single round of 16-byte loads
+// per thread instead of 14 dependent-latency rounds in one warp.
+__global__ void __launch_bounds__(256)
+rmsnorm_rowblock_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const bf16* __restrict__ weight, int dim, float eps,
+                        const int* __restrict__ row_idx) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int row = blockIdx.x;
+    const size_t in_row = row_idx ? static_cast<size_t>(row_idx[row]) : static_cast<size_t>(row);
+    const int nchunk = dim >> 3;
+    const uint4* xp = reinterpret_cast<const uint4*>(x + in_row * dim);
+    const uint4* wp = reinterpret_cast<const uint4*>(weight);
+    constexpr int MAXC = 4;  // dim <= 8192
+    float v[MAXC][8], w[MAXC][8];
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+        const int c = threadIdx.x + 256 * i;
+        if (c < nchunk) {
+            unpack8(xp[c], v[i]);
+            unpack8(__ldg(wp + c), w[i]);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) sq += v[i][e] * v[i][e];
+        }
+    }
+    __shared__ float part[8];
+    sq = warp_sum(sq);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = sq;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot += part[i];
+    const float rstd = rsqrtf(tot / dim + eps);
+    uint4* yp = reinterpret_cast<uint4*>(y + static_cast<size_t>(row) * dim);
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+        const int c = threadIdx.x + 256 * i;
+        if (c < nchunk) {
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = w[i][e] * bf16_round(v[i][e] * rstd);
+            yp[c] = pack8(o);
+        }
+    }
+}
+
 int rmsnorm(cudaStream_t stream, const bf16* x, bf16* y, const bf16* weight, int rows, int dim, float eps,
             const int* row_idx) {
     AF3_REQUIRE(dim % 8 == 0 && dim <= NORM_MAXV * 256, "rmsnorm: dim must be a multiple of 8 and <= 4096");
     if (rows <= 0) return 0;
-    AF3_CHECK_CUDA(launch_kernel(rmsnorm_kernel, dim3(ceil_div(rows, 8)), dim3(256), 0, stream, x, y, weight, rows, dim, eps,
-                                 row_idx));
+    if (rows <= 1024) {
+        AF3_CHECK_CUDA(launch_kernel(rmsnorm_rowblock_kernel, dim3(rows), dim3(256), 0, stream, x, y, weight, dim, eps, row_idx));
+        return 0;
+    }
+    const int need = ceil_div(dim >> 3, 32);
+    if (need <= 5)
+        AF3_CHECK_CUDA(launch_kernel(rmsnorm_kernel<5>, dim3(ceil_div(rows, 8)), dim3(256), 0, stream, x, y, weight, rows, dim, eps, row_idx));
+    else if (need <= 14)
+        AF3_CHECK_CUDA(launch_kernel(rmsnorm_kernel<14>, dim3(ceil_div(rows, 8)), dim3(256), 0, stream, x, y, weight, rows, dim, eps, row_idx));
+    else
+        AF3_CHECK_CUDA(launch_kernel(rmsnorm_kernel<16>, dim3(ceil_div(rows, 8)), dim3(256), 0, stream, x, y, weight, rows, dim, eps, row_idx));
     return 0;
 }
 
@@ -265,8 +337,11 @@ int pack_gate_up(cudaStream_t stream, const bf16* gate, const bf16* up, bf16* pa
 // ---------------------------------------------------------------------------------------------------------
 // Rotary embedding + KV append ([O] Q2M:100-146 rotate-half RoPE with fp32 tables cast to bf16; CACHE:119-120).
 // Every bf16 op of the reference rounds: q*cos, rotate_half(q)*sin and their sum are each rounded to bf16.
-// One thread = one (token, 8-wide d chunk of the first half): cos/sin are computed once and reused for every head;
-// all accesses are 16-byte vectors (chunk d..d+7 and its rotate-half partner d+D/2..d+D/2+7).
+// HEAD_PAR = false (prefill): one thread = one (token, 8-wide d chunk of the first half); cos/sin are computed once and
+// reused for every head.  HEAD_PAR = true (decode, few tokens): one thread = one (token, head, chunk) so the few
+// tokens still spread over thousands of threads instead of a 32-iteration dependent loop per thread.
+// All accesses are 16-byte vectors (chunk d..d+7 and its rotate-half partner d+D/2..d+D/2+7).
+template <bool HEAD_PAR>
 __global__ void __launch_bounds__(256)
 rope_kv_append_kernel(bf16* __restrict__ qkv, bf16* __restrict__ k_cache, bf16* __restrict__ v_cache, int B, int T,
                       int H, int Hkv, int D, int Tmax, int pos0, const int* __restrict__ pos0_dev,
@@ -274,45 +349,55 @@ rope_kv_append_kernel(bf16* __restrict__ qkv, bf16* __restrict__ k_cache, bf16* 
     const int half = D >> 1;
     const int cpt = half >> 3;  // 8-wide chunks per token half
     const int heads = H + 2 * Hkv;
-    const long long total = static_cast<long long>(B) * T * cpt;
+    const long long total = static_cast<long long>(B) * T * cpt * (HEAD_PAR ? heads : 1);
     pdl_launch_dependents();
     pdl_wait();
     const int p0 = pos0_dev ? *pos0_dev : pos0;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int ch = static_cast<int>(i % cpt);
-        const long long bt = i / cpt;
+        long long rest = i;
+        int h_only = 0;
+        if (HEAD_PAR) {
+            h_only = static_cast<int>(rest % heads);
+            rest /= heads;
+        }
+        const int ch = static_cast<int>(rest % cpt);
+        const long long bt = rest / cpt;
         const int t = static_cast<int>(bt % T);
         const int b = static_cast<int>(bt / T);
         const int d0 = ch * 8;
         const int cpos = p0 + t;  // cache slot
-        int pos = cpos - (kv_start ? kv_start[b] : 0);
-        if (pos < 0) pos = 1;  // padded slot: position_ids.masked_fill_(mask == 0, 1) (GEN:721)
-        float c[8], sn[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const float fr = inv_freq[d0 + e] * static_cast<float>(pos);
-            c[e] = bf16_round(cosf(fr));
-            sn[e] = bf16_round(sinf(fr));
-        }
         bf16* tok = qkv + static_cast<size_t>(bt) * heads * D;
-        for (int h = 0; h < H + Hkv; ++h) {
-            bf16* row = tok + static_cast<size_t>(h) * D;
-            float x1[8], x2[8], o1[8], o2[8];
-            unpack8(*reinterpret_cast<const uint4*>(row + d0), x1);
-            unpack8(*reinterpret_cast<const uint4*>(row + d0 + half), x2);
+        const int h_beg = HEAD_PAR ? h_only : 0, h_end = HEAD_PAR ? h_only + 1 : heads;
+        if (h_beg < H + Hkv) {
+            int pos = cpos - (kv_start ? kv_start[b] : 0);
+            if (pos < 0) pos = 1;  // padded slot: position_ids.masked_fill_(mask == 0, 1) (GEN:721)
+            float c[8], sn[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                o1[e] = bf16_round(bf16_round(x1[e] * c[e]) + bf16_round(-x2[e] * sn[e]));
-                o2[e] = bf16_round(bf16_round(x2[e] * c[e]) + bf16_round(x1[e] * sn[e]));
+                const float fr = inv_freq[d0 + e] * static_cast<float>(pos);
+                c[e] = bf16_round(cosf(fr));
+                sn[e] = bf16_round(sinf(fr));
             }
-            bf16* dst = row;
-            if (h >= H) dst = k_cache + ((static_cast<size_t>(b) * Hkv + (h - H)) * Tmax + cpos) * D;
-            *reinterpret_cast<uint4*>(dst + d0) = pack8(o1);
-            *reinterpret_cast<uint4*>(dst + d0 + half) = pack8(o2);
+            for (int h = h_beg; h < min(h_end, H + Hkv); ++h) {
+                bf16* row = tok + static_cast<size_t>(h) * D;
+                float x1[8], x2[8], o1[8], o2[8];
+                unpack8(*reinterpret_cast<const uint4*>(row + d0), x1);
+                unpack8(*reinterpret_cast<const uint4*>(row + d0 + half), x2);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    o1[e] = bf16_round(bf16_round(x1[e] * c[e]) + bf16_round(-x2[e] * sn[e]));
+                    o2[e] = bf16_round(bf16_round(x2[e] * c[e]) + bf16_round(x1[e] * sn[e]));
+                }
+                bf16* dst = row;
+                if (h >= H) dst = k_cache + ((static_cast<size_t>(b) * Hkv + (h - H)) * Tmax + cpos) * D;
+                *reinterpret_cast<uint4*>(dst + d0) = pack8(o1);
+                *reinterpret_cast<uint4*>(dst + d0 + half) = pack8(o2);
+            }
         }
-        for (int hk = 0; hk < Hkv; ++hk) {  // value heads: plain copy into the cache
-            const bf16* row = tok + static_cast<size_t>(H + Hkv + hk) * D;
+        for (int h = max(h_beg, H + Hkv); h < h_end; ++h) {  // value heads: plain copy into the cache
+            const int hk = h - H - Hkv;
+            const bf16* row = tok + static_cast<size_t>(h) * D;
             bf16* dst = v_cache + ((static_cast<size_t>(b) * Hkv + hk) * Tmax + cpos) * D;
             *reinterpret_cast<uint4*>(dst + d0) = *reinterpret_cast<const uint4*>(row + d0);
             *reinterpret_cast<uint4*>(dst + d0 + half) = *reinterpret_cast<const uint4*>(row + d0 + half);
@@ -324,11 +409,17 @@ int rope_kv_append(cudaStream_t stream, bf16* qkv, bf16* k_cache, bf16* v_cache,
                    int Tmax, int pos0, const int* pos0_dev, const int* kv_start, const float* inv_freq) {
     AF3_REQUIRE(D % 16 == 0 && inv_freq, "rope: head dim must be a multiple of 16 / missing inv_freq");
     AF3_REQUIRE(pos0_dev || pos0 + T <= Tmax, "rope: KV cache overflow");
-    const long long total = static_cast<long long>(B) * T * (D / 16);
-    if (total <= 0) return 0;
+    const long long tok_chunks = static_cast<long long>(B) * T * (D / 16);
+    if (tok_chunks <= 0) return 0;
+    const bool head_par = tok_chunks < 8192;  // decode steps / short prompts
+    const long long total = tok_chunks * (head_par ? (H + 2 * Hkv) : 1);
     const int grid = static_cast<int>(((total + 255) / 256) < 148ll * 32 ? ((total + 255) / 256) : 148ll * 32);
-    AF3_CHECK_CUDA(launch_kernel(rope_kv_append_kernel, dim3(grid), dim3(256), 0, stream, qkv, k_cache, v_cache, B, T, H, Hkv, D,
-                                 Tmax, pos0, pos0_dev, kv_start, inv_freq));
+    if (head_par)
+        AF3_CHECK_CUDA(launch_kernel(rope_kv_append_kernel<true>, dim3(grid), dim3(256), 0, stream, qkv, k_cache, v_cache, B, T, H,
+                                     Hkv, D, Tmax, pos0, pos0_dev, kv_start, inv_freq));
+    else
+        AF3_CHECK_CUDA(launch_kernel(rope_kv_append_kernel<false>, dim3(grid), dim3(256), 0, stream, qkv, k_cache, v_cache, B, T, H,
+                                     Hkv, D, Tmax, pos0, pos0_dev, kv_start, inv_freq));
     return 0;
 }
 

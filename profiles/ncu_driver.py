@@ -2,7 +2,8 @@
 runs warm-up steps unprofiled, then ONE step between cudaProfilerStart/Stop.
   launch list : ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none -c 1600 --csv --log-file X python profiles/ncu_driver.py
   top kernel  : ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:gemm_kernel -c 3 -o X python profiles/ncu_driver.py
-Decode steps are limited (AF3_NCU_NEW_TOKENS, default 3) so the profiled region stays short; eager decode (no graph)."""
+Decode steps are limited (AF3_NCU_NEW_TOKENS, default 3) so the profiled region stays short; eager decode unless
+AF3_NCU_GRAPH=1 (then ncu --graph-profiling node times the kernel nodes of the replayed decode graph)."""
 import os
 import sys
 from pathlib import Path
@@ -30,7 +31,8 @@ mask = torch.ones_like(ids)
 def step():
     feats = fe.from_device_waveform(wave, [wave_np.shape[1]] * bench.B_PER_GPU)
     return model.generate(input_ids=ids, attention_mask=mask, input_features=feats["input_features"],
-                          input_features_mask=feats["input_features_mask"], max_new_tokens=new, use_cuda_graph=False)
+                          input_features_mask=feats["input_features_mask"], max_new_tokens=new,
+                          use_cuda_graph=os.environ.get("AF3_NCU_GRAPH", "0") == "1")
 
 
 step()
