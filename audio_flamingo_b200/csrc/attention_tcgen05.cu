@@ -41,7 +41,7 @@ struct AttnCfg {
     static constexpr int TILE_BYTES = AT_BN * D * 2;       // one K or V tile
     static constexpr int Q_BYTES = AT_BM * D * 2;
     static constexpr int P_BYTES = AT_BM * AT_BN * 2;
-    static constexpr int SMEM_BYTES = Q_BYTES + P_BYTES + AT_NSTG * TILE_BYTES + 1024 + 128;
+    static constexpr int SMEM_BYTES = Q_BYTES + P_BYTES + AT_NSTG * TILE_BYTES + 1024 + 128 + 768 * 4;
     static constexpr int TMEM_COLS = 256;                  // S: 128 cols, O: D cols
 };
 
@@ -56,7 +56,7 @@ __device__ __forceinline__ void attn_tile_range(const AttnArgs& a, int b, int q0
 }
 
 template <int D>
-__global__ void __launch_bounds__(192)
+__global__ void __launch_bounds__(320, 2)
 attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                  const __grid_constant__ CUtensorMap map_v, const AttnArgs a) {
     using Cfg = AttnCfg<D>;
@@ -74,6 +74,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     uint64_t* p_full = s_full + 1;
     uint64_t* o_full = p_full + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+    float* sMax = reinterpret_cast<float*>(bars + 16);  // [2 tiles][2 halves][128 rows] maxima + [2][128] row sums
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * AT_BM, h = blockIdx.y, b = blockIdx.z;
@@ -89,7 +90,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             mbar_init(&kv_empty[i], 1);
         }
         mbar_init(s_full, 1);
-        mbar_init(p_full, 128);
+        mbar_init(p_full, 256);
         mbar_init(o_full, 1);
         fence_barrier_init();
     }
@@ -186,15 +187,22 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         }
         __syncwarp();
     } else {
+        // ---- softmax: 8 warps, TWO threads per query row: warp w handles TMEM lane quarter (w & 3) and the key columns
+        //      [half*64, half*64+64) of S with half = (w - 2) >> 2 (4 softmax warps per SM sub-partition with 2 CTAs/SM:
+        //      enough independent instruction streams to hide the SFU / TMEM / shared-memory latencies)
         const int qd = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int row = qd * 32 + lane;        // query row within the tile = TMEM lane
         const int qi = q0 + row;               // query index
         const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
         const int kvl = a.kv_len ? min(a.kv_len[b], a.Tk) : a.Tk;
         const int kvs = a.kv_start ? a.kv_start[b] : 0;
         const int causal_hi = a.causal ? qi + (a.Tk - a.Tq) : 0x7fffffff;  // last visible key (inclusive)
-        float m_ref = -INFINITY, l_run = 0.f;
+        float m_ref = -INFINITY, l_run = 0.f;   // l_run: partial row sum over this thread's columns
         const float sl2 = a.scale_log2;
+        const uint32_t s_col = tmem_S + lane_off + half * 64;
+        constexpr int OC = D / 2;               // O columns owned by this thread (rescale / epilogue)
+        const uint32_t o_col = tmem_O + lane_off + half * OC;
 
         for (int t = 0; t < n_tiles; ++t) {
             const int k0 = (j_lo + t) * AT_BN;
@@ -204,24 +212,24 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             // keys visible to this row inside the tile: local index in [vlo, vhi]  (one unsigned compare per element)
             const int vlo = max(kvs - k0, 0);
             const int vhi = min(min(kvl - 1, causal_hi) - k0, AT_BN - 1);
-            const uint32_t vspan = static_cast<uint32_t>(vhi - vlo);  // wraps to huge when the row sees no key: handled below
+            const uint32_t vspan = static_cast<uint32_t>(vhi - vlo);
             const bool row_empty = vhi < vlo;
-            // ---- pass 1: row max (two 32-column TMEM loads in flight)
-            float m_tile = -INFINITY;
-#pragma unroll
-            for (int c = 0; c < AT_BN / 64; ++c) {
+            const int cbase = half * 64;        // first local key index of this thread's columns
+            // ---- pass 1: partial row max over 64 columns
+            float m_part;
+            {
                 uint32_t v0[32], v1[32];
-                tmem_ld32(tmem_S + lane_off + c * 64, v0);
-                tmem_ld32(tmem_S + lane_off + c * 64 + 32, v1);
+                tmem_ld32(s_col, v0);
+                tmem_ld32(s_col + 32, v1);
                 tmem_ld_wait();
                 float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
                 if (need_mask) {
 #pragma unroll
                     for (int e = 0; e < 32; e += 2) {
-                        const bool ok0 = static_cast<uint32_t>(c * 64 + e - vlo) <= vspan;
-                        const bool ok1 = static_cast<uint32_t>(c * 64 + e + 1 - vlo) <= vspan;
-                        const bool ok2 = static_cast<uint32_t>(c * 64 + 32 + e - vlo) <= vspan;
-                        const bool ok3 = static_cast<uint32_t>(c * 64 + 33 + e - vlo) <= vspan;
+                        const bool ok0 = static_cast<uint32_t>(cbase + e - vlo) <= vspan;
+                        const bool ok1 = static_cast<uint32_t>(cbase + e + 1 - vlo) <= vspan;
+                        const bool ok2 = static_cast<uint32_t>(cbase + 32 + e - vlo) <= vspan;
+                        const bool ok3 = static_cast<uint32_t>(cbase + 33 + e - vlo) <= vspan;
                         mx0 = fmaxf(mx0, ok0 ? __uint_as_float(v0[e]) : -INFINITY);
                         mx1 = fmaxf(mx1, ok1 ? __uint_as_float(v0[e + 1]) : -INFINITY);
                         mx2 = fmaxf(mx2, ok2 ? __uint_as_float(v1[e]) : -INFINITY);
@@ -236,9 +244,13 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                         mx3 = fmaxf(mx3, __uint_as_float(v1[e + 1]));
                     }
                 }
-                m_tile = fmaxf(m_tile, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
+                m_part = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+                if (need_mask && row_empty) m_part = -INFINITY;
             }
-            if (need_mask && row_empty) m_tile = -INFINITY;
+            // exchange the two half-row maxima (double-buffered by tile parity) -> full-row max
+            sMax[(t & 1) * 256 + half * 128 + row] = m_part;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            float m_tile = fmaxf(m_part, sMax[(t & 1) * 256 + (half ^ 1) * 128 + row]);
             m_tile *= sl2;  // sl2 > 0: max commutes with the scale
             const float m_new = fmaxf(m_ref, m_tile);
             // ---- wait until P.V of the previous tile retired: P buffer and O are ours again
@@ -247,19 +259,19 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 mbar_wait(o_full, (t - 1) & 1);
                 tc_fence_after();
                 const bool grow = (m_new - m_ref) > 8.0f;  // also true when m_ref == -inf and m_new finite
-                if (__any_sync(0xffffffffu, grow)) {
+                if (__any_sync(0xffffffffu, grow)) {   // both threads of a row take the same decision (same m_new, m_ref)
                     if (grow) {
                         alpha = (m_ref == -INFINITY) ? 0.f : exp2f(m_ref - m_new);
                         m_ref = m_new;
                     }
 #pragma unroll 1
-                    for (int c = 0; c < D / 32; ++c) {
+                    for (int c = 0; c < OC / 32; ++c) {
                         uint32_t o[32];
-                        tmem_ld32(tmem_O + lane_off + c * 32, o);
+                        tmem_ld32(o_col + c * 32, o);
                         tmem_ld_wait();
 #pragma unroll
                         for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
-                        tmem_st32(tmem_O + lane_off + c * 32, o);
+                        tmem_st32(o_col + c * 32, o);
                     }
                     tmem_st_wait();
                 }
@@ -267,61 +279,58 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 m_ref = m_new;
             }
             const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
-            // ---- pass 2: p = 2^(s*scale - m) -> bf16 P in the K-major 128B-swizzled layout, row sums in fp32
+            // ---- pass 2: p = 2^(s*scale - m) -> bf16 P (swizzle block `half` of the K-major A tile), fp32 partial row sum
             float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+            uint8_t* prow = sP + half * 16384 + row * 128;
 #pragma unroll
-            for (int c = 0; c < AT_BN / 64; ++c) {
-                uint32_t v0[32], v1[32];
-                tmem_ld32(tmem_S + lane_off + c * 64, v0);
-                tmem_ld32(tmem_S + lane_off + c * 64 + 32, v1);
+            for (int hh = 0; hh < 2; ++hh) {
+                uint32_t v[32];
+                tmem_ld32(s_col + hh * 32, v);
                 tmem_ld_wait();
-                uint8_t* prow = sP + c * 16384 + row * 128;  // keys c*64 .. c*64+63 = swizzle block c
+                uint32_t pk[16];
 #pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    uint32_t(&v)[32] = hh ? v1 : v0;
-                    uint32_t pk[16];
-#pragma unroll
-                    for (int e = 0; e < 32; e += 2) {
-                        float p0 = fast_exp2(fmaf(__uint_as_float(v[e]), sl2, neg_m));
-                        float p1 = fast_exp2(fmaf(__uint_as_float(v[e + 1]), sl2, neg_m));
-                        if (need_mask) {
-                            p0 = (static_cast<uint32_t>(c * 64 + hh * 32 + e - vlo) <= vspan && !row_empty) ? p0 : 0.f;
-                            p1 = (static_cast<uint32_t>(c * 64 + hh * 32 + e + 1 - vlo) <= vspan && !row_empty) ? p1 : 0.f;
-                        }
-                        if (e & 2) {
-                            l2 += p0;
-                            l3 += p1;
-                        } else {
-                            l0 += p0;
-                            l1 += p1;
-                        }
-                        pk[e >> 1] = pack_bf16x2(p0, p1);
+                for (int e = 0; e < 32; e += 2) {
+                    float p0 = fast_exp2(fmaf(__uint_as_float(v[e]), sl2, neg_m));
+                    float p1 = fast_exp2(fmaf(__uint_as_float(v[e + 1]), sl2, neg_m));
+                    if (need_mask) {
+                        p0 = (static_cast<uint32_t>(cbase + hh * 32 + e - vlo) <= vspan && !row_empty) ? p0 : 0.f;
+                        p1 = (static_cast<uint32_t>(cbase + hh * 32 + e + 1 - vlo) <= vspan && !row_empty) ? p1 : 0.f;
                     }
-#pragma unroll
-                    for (int g = 0; g < 4; ++g)
-                        *reinterpret_cast<uint4*>(prow + (((hh * 4 + g) ^ (row & 7)) << 4)) =
-                            make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+                    if (e & 2) {
+                        l2 += p0;
+                        l3 += p1;
+                    } else {
+                        l0 += p0;
+                        l1 += p1;
+                    }
+                    pk[e >> 1] = pack_bf16x2(p0, p1);
                 }
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                    *reinterpret_cast<uint4*>(prow + (((hh * 4 + g) ^ (row & 7)) << 4)) =
+                        make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
             }
-            const float l_tile = (l0 + l1) + (l2 + l3);
-            l_run = l_run * alpha + l_tile;
+            l_run = l_run * alpha + ((l0 + l1) + (l2 + l3));
             fence_proxy_async_smem();
             tc_fence_before();
             mbar_arrive(p_full);
         }
 
-        // ---- epilogue: O / l -> bf16 -> global
+        // ---- epilogue: O / l -> bf16 -> global; the two threads of a row add their partial sums and split the D columns
         if (n_tiles > 0) {
             mbar_wait(o_full, (n_tiles - 1) & 1);
             tc_fence_after();
         }
-        const float inv_l = (l_run > 0.f) ? 1.0f / l_run : 0.f;
-        bf16* orow = a.out + (static_cast<size_t>(b) * a.Tq + qi) * a.ldo + h * D;
+        sMax[512 + half * 128 + row] = l_run;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float l_tot = l_run + sMax[512 + (half ^ 1) * 128 + row];
+        const float inv_l = (l_tot > 0.f) ? 1.0f / l_tot : 0.f;
+        bf16* orow = a.out + (static_cast<size_t>(b) * a.Tq + qi) * a.ldo + h * D + half * OC;
 #pragma unroll 1
-        for (int c = 0; c < D / 32; ++c) {
+        for (int c = 0; c < OC / 32; ++c) {
             uint32_t o[32];
             if (n_tiles > 0) {
-                tmem_ld32(tmem_O + lane_off + c * 32, o);
+                tmem_ld32(o_col + c * 32, o);
                 tmem_ld_wait();
             } else {
 #pragma unroll
@@ -357,7 +366,7 @@ static int launch_attention(cudaStream_t stream, const CUtensorMap& mq, const CU
         configured = true;
     }
     dim3 grid(ceil_div(a.Tq, AT_BM), a.H, B);
-    kern<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(mq, mk, mv, a);
+    kern<<<grid, 320, Cfg::SMEM_BYTES, stream>>>(mq, mk, mv, a);
     AF3_CHECK_LAUNCH();
     return 0;
 }

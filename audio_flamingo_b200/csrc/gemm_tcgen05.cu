@@ -19,6 +19,8 @@
 #include "common.h"
 #include "ptx.cuh"
 
+#include <cstdlib>
+
 namespace af3 {
 
 enum : int { EPI_BIAS = 1, EPI_GELU = 2, EPI_RESID = 4, EPI_SWIGLU = 8, EPI_F32OUT = 16 };
@@ -53,7 +55,8 @@ struct GemmCfg {
     static constexpr int ACC_COLS = NA * BN;
     static constexpr int TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128) ? 128 : (2 * ACC_COLS <= 256) ? 256 : 512;
     // normal mode: 4 epilogue warps x 2 buffers x (32 rows x 128 B) staging for the TMA-store epilogue
-    static constexpr int EPI_STAGE_BYTES = SWAP ? 0 : 4 * 2 * 4096;
+    // swap mode: one [32 tokens x 128 features] bf16 tile to transpose the accumulator for token-major vector I/O
+    static constexpr int EPI_STAGE_BYTES = SWAP ? 32 * 128 * 2 : 4 * 2 * 4096;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
     static_assert(2 * ACC_COLS <= 512, "TMEM budget");
     static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
@@ -500,22 +503,79 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
                         }
                     }
                     const int tok0 = c * BN + ch * 32;
+                    if constexpr (BN == 32) {
+                        if (!(flags & EPI_F32OUT) && (a.ldo & 7) == 0 && (!(flags & EPI_RESID) || ((a.ld_res & 7) == 0 && a.res_period == 0))) {
+                            // ---- transposed epilogue: this thread owns feature `feat` for 32 tokens, but the output (and the
+                            // residual) are token-major.  Pre-residual values go through a [32 tok][128 feat] bf16 smem tile so
+                            // that global traffic is 16-byte vectors along the feature dimension (4 loads + 4 stores per thread
+                            // instead of 32 + 32 scalar ones whose latencies ptxas otherwise serialises).
+                            bf16* tile = reinterpret_cast<bf16*>(epi_stage);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                float y;
+                                if constexpr (NA == 2)
+                                    y = epi_swiglu(__uint_as_float(v[j]), __uint_as_float(u[j]));
+                                else
+                                    y = epi_elem(__uint_as_float(v[j]), flags & ~EPI_RESID, bias, 0.f);
+                                tile[j * 128 + row_in_tile] = __float2bfloat16_rn(y);
+                            }
+                            asm volatile("bar.sync 2, 128;" ::: "memory");
+                            const int et = threadIdx.x - 64;             // 0..127 within the epilogue warps
+                            const int tok = tok0 + (et >> 2);
+                            const int f0 = r * 128 + (et & 3) * 32;      // first of this thread's 32 features
+                            if (tok < a.n_tok) {
+                                const uint4* tp = reinterpret_cast<const uint4*>(tile + (et >> 2) * 128 + (et & 3) * 32);
+                                bf16* op = reinterpret_cast<bf16*>(a.out) + static_cast<size_t>(tok) * a.ldo + f0;
+                                uint4 rv[4];
+                                if (flags & EPI_RESID) {
+                                    const uint4* rp = reinterpret_cast<const uint4*>(a.resid + static_cast<size_t>(tok) * a.ld_res + f0);
+#pragma unroll
+                                    for (int g4 = 0; g4 < 4; ++g4)
+                                        if (f0 + g4 * 8 < a.n_feat) rv[g4] = __ldcg(rp + g4);
+                                }
+#pragma unroll
+                                for (int g4 = 0; g4 < 4; ++g4) {
+                                    if (f0 + g4 * 8 < a.n_feat) {   // n_feat is a multiple of 8 on this path (ldo % 8 == 0)
+                                        uint4 yv = tp[g4];
+                                        if (flags & EPI_RESID) {
+                                            const __nv_bfloat162* yh = reinterpret_cast<const __nv_bfloat162*>(&yv);
+                                            const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rv[g4]);
+                                            uint32_t o4[4];
+#pragma unroll
+                                            for (int e = 0; e < 4; ++e) {
+                                                const float2 yf = __bfloat1622float2(yh[e]), rf = __bfloat1622float2(rh[e]);
+                                                o4[e] = pack_bf16x2(yf.x + rf.x, yf.y + rf.y);
+                                            }
+                                            yv = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+                                        }
+                                        reinterpret_cast<uint4*>(op)[g4] = yv;
+                                    }
+                                }
+                            }
+                            asm volatile("bar.sync 2, 128;" ::: "memory");  // tile may be rewritten by the next work item
+                            continue;
+                        }
+                    }
                     if (feat_ok) {
+                        float res[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int tok = tok0 + j;
+                            res[j] = 0.f;
+                            if (NA == 1 && (flags & EPI_RESID) && tok < a.n_tok) {
+                                const int rr = (a.res_period > 0) ? (tok % a.res_period) : tok;
+                                res[j] = __bfloat162float(__ldcg(a.resid + static_cast<size_t>(rr) * a.ld_res + feat));
+                            }
+                        }
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const int tok = tok0 + j;
                             if (tok < a.n_tok) {
                                 float x;
-                                if constexpr (NA == 2) {
+                                if constexpr (NA == 2)
                                     x = epi_swiglu(__uint_as_float(v[j]), __uint_as_float(u[j]));
-                                } else {
-                                    float res = 0.f;
-                                    if (flags & EPI_RESID) {
-                                        const int rr = (a.res_period > 0) ? (tok % a.res_period) : tok;
-                                        res = __bfloat162float(a.resid[static_cast<size_t>(rr) * a.ld_res + feat]);
-                                    }
-                                    x = epi_elem(__uint_as_float(v[j]), flags, bias, res);
-                                }
+                                else
+                                    x = epi_elem(__uint_as_float(v[j]), flags, bias, res[j]);
                                 if (flags & EPI_F32OUT)
                                     reinterpret_cast<float*>(a.out)[static_cast<size_t>(tok) * a.ldo + feat] = x;
                                 else
@@ -654,6 +714,8 @@ int gemm_bf16(cudaStream_t stream, const bf16* x, int ldx, const bf16* w, int ld
     const int kb_total = ceil_div(K, BK);
     if (workspace && workspace_bytes >= gemm_workspace_bytes() && tiles * 2 <= sm_count() && tiles <= 4096) {
         int s = sm_count() / tiles;
+        static const int forced = [] { const char* e = getenv("AF3_KSPLIT"); return e ? atoi(e) : 0; }();  // experiments only
+        if (forced > 0) s = forced;
         if (s > kb_total / 4) s = kb_total / 4;  // keep at least 4 k-blocks per split
         if (s > 16) s = 16;
         if (s >= 2 && static_cast<size_t>(tiles) * s * BN * 128 * sizeof(float) <= (8u << 20)) {
