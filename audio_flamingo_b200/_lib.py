@@ -31,6 +31,8 @@ SIGNATURES = {
     "af3_rmsnorm": (_i, [_p, _p, _p, _p, _i, _i, _f, _p]),
     "af3_attention": (_i, [_p, _p, _i, _p, _p, _i, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _f, _i, _p, _p]),
     "af3_rope_kv_append": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "af3_rope_table": (_i, [_p, _p, _i, _i, _p, _p, _p]),
+    "af3_gemm_qkv_rope": (_i, [_p, _p, _i, _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i, _p, _p, _sz]),
     "af3_decode_attention": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _f]),
     "af3_decode_attention_scratch_bytes": (_sz, [_i, _i, _i, _i]),
     "af3_embed_scatter": (_i, [_p, _p, _i, _p, _i, _i64, _p, _i, _i, _p, _p, _p, _p]),

@@ -5,9 +5,17 @@
 
 namespace af3 {
 const char* last_error_cstr();
+struct RopeEpilogue {
+    const float* cs;
+    bf16* k_cache;
+    bf16* v_cache;
+    const int* pos;
+    int H, Hkv, Tmax;
+};
 int gemm_bf16(cudaStream_t stream, const bf16* x, int ldx, const bf16* w, int ldw, void* out, int ldo, int n_tok,
               int n_feat, int K, int flags, const bf16* bias, const bf16* resid, int ld_res, int res_period,
-              void* workspace, size_t workspace_bytes);
+              void* workspace, size_t workspace_bytes, const RopeEpilogue* rope);
+int rope_table(cudaStream_t stream, float* cs, int B, int D, const int* pos_dev, const int* kv_start, const float* inv_freq);
 size_t gemm_workspace_bytes();
 int logmel(cudaStream_t stream, const float* wave, int n_win, int n_samples, const float* hann, const float* table,
            const float* filt, const int* klo, const int* khi, float* out, int* win_max);
@@ -46,7 +54,7 @@ void af3_set_pdl(int enable) { af3::set_pdl(enable != 0); }
 int af3_gemm_bf16(void* stream, const void* x, int ldx, const void* w, int ldw, void* out, int ldo, int n_tok, int n_feat,
                   int K, int flags, const void* bias, const void* resid, int ld_res, int res_period) {
     return af3::gemm_bf16(S(stream), B16(x), ldx, B16(w), ldw, out, ldo, n_tok, n_feat, K, flags, B16(bias), B16(resid),
-                          ld_res, res_period, nullptr, 0);
+                          ld_res, res_period, nullptr, 0, nullptr);
 }
 
 size_t af3_gemm_workspace_bytes(void) { return af3::gemm_workspace_bytes(); }
@@ -55,7 +63,20 @@ int af3_gemm_bf16_ws(void* stream, const void* x, int ldx, const void* w, int ld
                      int n_feat, int K, int flags, const void* bias, const void* resid, int ld_res, int res_period,
                      void* workspace, size_t workspace_bytes) {
     return af3::gemm_bf16(S(stream), B16(x), ldx, B16(w), ldw, out, ldo, n_tok, n_feat, K, flags, B16(bias), B16(resid),
-                          ld_res, res_period, workspace, workspace_bytes);
+                          ld_res, res_period, workspace, workspace_bytes, nullptr);
+}
+
+int af3_rope_table(void* stream, float* cs, int B, int D, const int* pos_dev, const int* kv_start, const float* inv_freq) {
+    return af3::rope_table(S(stream), cs, B, D, pos_dev, kv_start, inv_freq);
+}
+
+int af3_gemm_qkv_rope(void* stream, const void* x, int ldx, const void* w, int ldw, const void* bias, void* q_out, int ldo,
+                      int n_tok, int K, int H, int Hkv, int D, const float* rope_cs, void* k_cache, void* v_cache, int Tmax,
+                      const int* pos_dev, void* workspace, size_t workspace_bytes) {
+    if (D != 128) return af3::fail("af3_gemm_qkv_rope: head_dim must be 128");
+    af3::RopeEpilogue r{rope_cs, B16M(k_cache), B16M(v_cache), pos_dev, H, Hkv, Tmax};
+    return af3::gemm_bf16(S(stream), B16(x), ldx, B16(w), ldw, q_out, ldo, n_tok, (H + 2 * Hkv) * D, K,
+                          AF3_EPI_BIAS | 32, B16(bias), nullptr, 0, 0, workspace, workspace_bytes, &r);
 }
 
 int af3_pack_gate_up(void* stream, const void* gate, const void* up, void* packed, int F, int K) {

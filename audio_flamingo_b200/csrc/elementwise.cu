@@ -423,6 +423,30 @@ int rope_kv_append(cudaStream_t stream, bf16* qkv, bf16* k_cache, bf16* v_cache,
     return 0;
 }
 
+// cos/sin table of ONE decode step for the RoPE-fused q/k/v projection epilogue: cs[b][i] = (bf16(cos), bf16(sin)) of
+// inv_freq[i] * position(b), position = slot - kv_start[b] (Q2M:100-113; identical for all layers of the step).
+__global__ void rope_table_kernel(float2* __restrict__ cs, int B, int half, const int* __restrict__ pos_dev,
+                                  const int* __restrict__ kv_start, const float* __restrict__ inv_freq) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * half) return;
+    const int b = i / half, d = i - b * half;
+    int pos = *pos_dev - (kv_start ? kv_start[b] : 0);
+    if (pos < 0) pos = 1;
+    const float fr = inv_freq[d] * static_cast<float>(pos);
+    cs[i] = make_float2(bf16_round(cosf(fr)), bf16_round(sinf(fr)));
+}
+
+int rope_table(cudaStream_t stream, float* cs, int B, int D, const int* pos_dev, const int* kv_start, const float* inv_freq) {
+    AF3_REQUIRE(D % 2 == 0 && pos_dev && inv_freq, "rope_table: bad arguments");
+    const int n = B * (D / 2);
+    if (n <= 0) return 0;
+    AF3_CHECK_CUDA(launch_kernel(rope_table_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, stream, reinterpret_cast<float2*>(cs), B,
+                                 D / 2, pos_dev, kv_start, inv_freq));
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Embedding gather + audio scatter ([O] AF3M:557 embed_tokens; :469-473 valid-frame select; :563-566 masked_scatter).
 // Kernel 1 (one CTA): exclusive scan of (ids == audio_token_id) over the flattened prompt -> ordinal of each audio

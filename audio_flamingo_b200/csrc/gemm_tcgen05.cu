@@ -23,7 +23,7 @@
 
 namespace af3 {
 
-enum : int { EPI_BIAS = 1, EPI_GELU = 2, EPI_RESID = 4, EPI_SWIGLU = 8, EPI_F32OUT = 16 };
+enum : int { EPI_BIAS = 1, EPI_GELU = 2, EPI_RESID = 4, EPI_SWIGLU = 8, EPI_F32OUT = 16, EPI_ROPE = 32 };
 
 struct GemmArgs {
     int R, C, K;  // extents of row operand, col operand, reduction
@@ -39,6 +39,14 @@ struct GemmArgs {
     // split-K (swap mode only): each output tile is computed by k_splits CTAs over disjoint K ranges; partial fp32
     // tiles go to `ws`, the CTA that arrives last (per-tile counter) sums them in split order (deterministic) and
     // runs the fused epilogue.  Fills the 148 SMs when the weight matrix has only 28-36 row tiles (decode step).
+    // EPI_ROPE (few-token q/k/v projection of the decode step, one 128-row tile = one head): rotary embedding and the
+    // KV-cache append are applied in the epilogue ([O] Q2M:100-146, CACHE:119-120) -- q heads go to `out`, k / v heads
+    // straight into the cache at slot *rope_pos.
+    const float2* rope_cs;   // [n_tok][64] (cos, sin), bf16-rounded
+    bf16* k_cache;
+    bf16* v_cache;
+    const int* rope_pos;     // device int: cache slot of this step
+    int rope_H, rope_Hkv, rope_Tmax;
     int tma_epi;    // normal mode: stage the output tile in smem and write it with TMA (coalesced); residual via TMA too
     int k_splits;
     float* ws;      // [tiles][k_splits][BN][128] fp32
@@ -523,7 +531,43 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
                             const int et = threadIdx.x - 64;             // 0..127 within the epilogue warps
                             const int tok = tok0 + (et >> 2);
                             const int f0 = r * 128 + (et & 3) * 32;      // first of this thread's 32 features
-                            if (tok < a.n_tok) {
+                            if ((flags & EPI_ROPE) && tok < a.n_tok) {
+                                // tile r = head r of the fused projection: [0,H) query, [H,H+Hkv) key, then value heads
+                                const int head = r, q4 = et & 3;
+                                const uint4* tp = reinterpret_cast<const uint4*>(tile + (et >> 2) * 128 + q4 * 32);
+                                bf16* op;
+                                if (head < a.rope_H)
+                                    op = reinterpret_cast<bf16*>(a.out) + static_cast<size_t>(tok) * a.ldo + f0;
+                                else {
+                                    const int hk = (head - a.rope_H) % a.rope_Hkv;
+                                    bf16* cache = (head < a.rope_H + a.rope_Hkv) ? a.k_cache : a.v_cache;
+                                    op = cache + ((static_cast<size_t>(tok) * a.rope_Hkv + hk) * a.rope_Tmax + *a.rope_pos) * 128 + q4 * 32;
+                                }
+                                if (head < a.rope_H + a.rope_Hkv) {
+                                    const uint4* pp = reinterpret_cast<const uint4*>(tile + (et >> 2) * 128 + (q4 ^ 2) * 32);  // d +- 64
+                                    const float2* cs = a.rope_cs + static_cast<size_t>(tok) * 64 + (q4 & 1) * 32;
+                                    const float sgn = (q4 < 2) ? -1.f : 1.f;  // rotate_half: -x[d+64] for d < 64, +x[d-64] otherwise
+#pragma unroll
+                                    for (int g4 = 0; g4 < 4; ++g4) {
+                                        const uint4 xv = tp[g4], pv = pp[g4];
+                                        const __nv_bfloat162* xh = reinterpret_cast<const __nv_bfloat162*>(&xv);
+                                        const __nv_bfloat162* ph = reinterpret_cast<const __nv_bfloat162*>(&pv);
+                                        uint32_t o4[4];
+#pragma unroll
+                                        for (int e = 0; e < 4; ++e) {
+                                            const float2 xf = __bfloat1622float2(xh[e]), pf = __bfloat1622float2(ph[e]);
+                                            const float2 c0 = __ldg(cs + g4 * 8 + 2 * e), c1 = __ldg(cs + g4 * 8 + 2 * e + 1);
+                                            const float o0 = bf16_round(xf.x * c0.x) + bf16_round(sgn * pf.x * c0.y);
+                                            const float o1 = bf16_round(xf.y * c1.x) + bf16_round(sgn * pf.y * c1.y);
+                                            o4[e] = pack_bf16x2(o0, o1);
+                                        }
+                                        reinterpret_cast<uint4*>(op)[g4] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int g4 = 0; g4 < 4; ++g4) reinterpret_cast<uint4*>(op)[g4] = tp[g4];
+                                }
+                            } else if (tok < a.n_tok) {
                                 const uint4* tp = reinterpret_cast<const uint4*>(tile + (et >> 2) * 128 + (et & 3) * 32);
                                 bf16* op = reinterpret_cast<bf16*>(a.out) + static_cast<size_t>(tok) * a.ldo + f0;
                                 uint4 rv[4];
@@ -635,6 +679,7 @@ static int launch(const CUtensorMap& mr, const CUtensorMap& mc, const CUtensorMa
             AF3_EPI_CASE(EPI_SWIGLU)
             AF3_EPI_CASE(EPI_F32OUT)
             AF3_EPI_CASE(EPI_BIAS | EPI_GELU | EPI_RESID)
+            AF3_EPI_CASE(EPI_BIAS | EPI_ROPE)
             default:
                 break;
         }
@@ -645,9 +690,17 @@ static int launch(const CUtensorMap& mr, const CUtensorMap& mc, const CUtensorMa
 
 size_t gemm_workspace_bytes() { return (8u << 20) + 4096 * sizeof(int); }
 
+struct RopeEpilogue {
+    const float* cs;
+    bf16* k_cache;
+    bf16* v_cache;
+    const int* pos;
+    int H, Hkv, Tmax;
+};
+
 int gemm_bf16(cudaStream_t stream, const bf16* x, int ldx, const bf16* w, int ldw, void* out, int ldo, int n_tok,
               int n_feat, int K, int flags, const bf16* bias, const bf16* resid, int ld_res, int res_period,
-              void* workspace, size_t workspace_bytes) {
+              void* workspace, size_t workspace_bytes, const RopeEpilogue* rope) {
     AF3_REQUIRE(n_tok > 0 && n_feat > 0 && K > 0, "gemm: empty problem");
     AF3_REQUIRE((K % 8) == 0 && (ldx % 8) == 0 && (ldw % 8) == 0, "gemm: K and pitches must be multiples of 8");
     AF3_REQUIRE(!(flags & EPI_BIAS) || bias, "gemm: bias flag without pointer");
@@ -666,6 +719,18 @@ int gemm_bf16(cudaStream_t stream, const bf16* x, int ldx, const bf16* w, int ld
     a.res_period = res_period;
     a.flags = flags;
     a.k_splits = 1;
+    if (flags & EPI_ROPE) {
+        AF3_REQUIRE(rope && rope->cs && rope->k_cache && rope->v_cache && rope->pos, "gemm: EPI_ROPE needs the rope arguments");
+        AF3_REQUIRE(n_tok <= 32 && n_feat == (rope->H + 2 * rope->Hkv) * 128 && (ldo % 8) == 0 && !(flags & (EPI_RESID | EPI_F32OUT | EPI_SWIGLU)),
+                    "gemm: EPI_ROPE is the few-token fused q/k/v projection with head_dim 128");
+        a.rope_cs = reinterpret_cast<const float2*>(rope->cs);
+        a.k_cache = rope->k_cache;
+        a.v_cache = rope->v_cache;
+        a.rope_pos = rope->pos;
+        a.rope_H = rope->H;
+        a.rope_Hkv = rope->Hkv;
+        a.rope_Tmax = rope->Tmax;
+    }
     CUtensorMap mx, mw, mo, mres;
     const bool swap = n_tok <= 64;
     if (!swap) {

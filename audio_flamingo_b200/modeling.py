@@ -290,17 +290,22 @@ class Qwen2ForCausalLM(nn.Module):
         """h [B*T, hid] residual stream, updated in place and returned."""
         H, Hkv, D = self.H, self.Hkv, self.D
         pos0 = cache.length
+        rope_cs = None
+        if decode:
+            if B > 32:
+                raise AF3Error("the fused decode step handles at most 32 sequences per GPU (shard the batch)")
+            rope_cs = ops.rope_table(B, D, cache.pos_dev, cache.kv_start, self._inv_freq)
         for li, (l, (wqkv, bqkv, wgu)) in enumerate(zip(self.model.layers, self._packed)):
             y = ops.rmsnorm(h, l.input_layernorm.weight, self.eps)
-            qkv = ops.linear(y, wqkv, bqkv)
             kc, vc = cache.k[li], cache.v[li]
             a = torch.empty((B * T, H * D), device=h.device, dtype=bf16)
             if decode:
-                ops.rope_kv_append(qkv, kc, vc, B=B, T=1, H=H, Hkv=Hkv, D=D, pos0=0, inv_freq=self._inv_freq,
-                                   kv_start=cache.kv_start, pos0_dev=cache.pos_dev)
+                # q/k/v projection with RoPE + KV append in the GEMM epilogue (rope table: once per step, below)
+                qkv = ops.qkv_rope_linear(y, wqkv, bqkv, kc, vc, H=H, Hkv=Hkv, D=D, rope_cs=rope_cs, pos_dev=cache.pos_dev)
                 ops.decode_attention(qkv, kc, vc, a, scratch, B=B, H=H, Hkv=Hkv, D=D, ctx_len=cache.ctx_dev,
                                      kv_start=cache.kv_start, scale=D ** -0.5)
             else:
+                qkv = ops.linear(y, wqkv, bqkv)
                 ops.rope_kv_append(qkv, kc, vc, B=B, T=T, H=H, Hkv=Hkv, D=D, pos0=pos0, inv_freq=self._inv_freq,
                                    kv_start=cache.kv_start)
                 ops.attention(qkv, kc, vc, a.view(B, T, H * D), B=B, H=H, Hkv=Hkv, D=D, Tq=T, Tk=pos0 + T, scale=D ** -0.5,

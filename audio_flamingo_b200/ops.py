@@ -256,22 +256,53 @@ def rope_kv_append(qkv, k_cache, v_cache, *, B, T, H, Hkv, D, pos0, inv_freq, kv
     _count(1)
 
 
+def rope_table(B, D, pos_dev, kv_start, inv_freq, out=None):
+    """(cos, sin) of this decode step for every sequence: fp32 [B, D/2, 2] (shared by all layers)."""
+    lib = _lib.load()
+    if out is None:
+        out = torch.empty((B, D // 2, 2), device=inv_freq.device, dtype=torch.float32)
+    with _Timed(("rope_table", B, D, 0, 0)):
+        check(lib.af3_rope_table(stream_ptr(), ptr(out), B, D, ptr(pos_dev), ptr(kv_start), ptr(inv_freq)), "af3_rope_table")
+    _count(1)
+    return out
+
+
+def qkv_rope_linear(x, w, bias, k_cache, v_cache, *, H, Hkv, D, rope_cs, pos_dev, out=None):
+    """Decode-step q/k/v projection with RoPE + KV append fused into the GEMM epilogue.  Returns the [n_tok, (H+2Hkv)*D]
+    buffer whose first H*D columns hold the rotated queries (k / v go straight into the caches)."""
+    lib = _lib.load()
+    _req(x, bf16, "x"), _req(w, bf16, "w"), _req(bias, bf16, "bias")
+    n_tok, K = x.shape
+    if out is None:
+        out = torch.empty((n_tok, (H + 2 * Hkv) * D), device=x.device, dtype=bf16)
+    ws = gemm_workspace(x.device)
+    Tmax = k_cache.shape[2]
+    with _Timed(("gemm", n_tok, (H + 2 * Hkv) * D, K, EPI_BIAS | 32)):
+        check(
+            lib.af3_gemm_qkv_rope(stream_ptr(), ptr(x), x.stride(0), ptr(w), w.stride(0), ptr(bias), ptr(out), out.stride(0), n_tok, K,
+                                  H, Hkv, D, ptr(rope_cs), ptr(k_cache), ptr(v_cache), Tmax, ptr(pos_dev), ptr(ws), ws.numel()),
+            "af3_gemm_qkv_rope",
+        )
+    _count(1)
+    return out
+
+
 def decode_attention(qkv, k_cache, v_cache, out, scratch, *, B, H, Hkv, D, ctx_len, kv_start, scale):
     lib = _lib.load()
     Tmax = k_cache.shape[2]
-    with _Timed(("decode_attention", B, H, Tmax, 0)):
+    with _Timed(("decode_attention", B, H, Tmax, 0)):  # one launch (the last chunk CTA merges the partials)
         check(
             lib.af3_decode_attention(stream_ptr(), ptr(qkv), ptr(k_cache), ptr(v_cache), ptr(out), ptr(scratch), B, H, Hkv, D,
                                      Tmax, ptr(ctx_len), ptr(kv_start), float(scale)),
             "af3_decode_attention",
         )
-    _count(2)
+    _count(1)
     return out
 
 
 def decode_attention_scratch(B, H, D, Tmax, device):
     n = _lib.load().af3_decode_attention_scratch_bytes(B, H, D, Tmax)
-    return torch.empty((n // 4,), device=device, dtype=torch.float32)
+    return torch.zeros(((n + 3) // 4,), device=device, dtype=torch.float32)  # zero: holds the arrival counters
 
 
 # ----------------------------------------------------------------------------------------------- glue

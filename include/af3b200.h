@@ -98,6 +98,16 @@ int af3_attention(void* stream, const void* q, int ldq, const void* k, const voi
 int af3_rope_kv_append(void* stream, void* qkv, void* k_cache, void* v_cache, int B, int T, int H, int Hkv, int D,
                        int Tmax, int pos0, const int* pos0_dev, const int* kv_start, const float* inv_freq);
 
+/* Decode-step fusion of the q/k/v projection with RoPE and the KV append (Q2M:199-215 + CACHE:119-120 in one kernel):
+ * out rows get the ROTATED query heads (columns [0, H*D)); rotated keys and the values go straight into the caches at
+ * slot *pos_dev.  rope_cs [n_tok][D/2][2] fp32 from af3_rope_table (once per step, shared by all layers).
+ * n_tok <= 32, D = 128, bias required (Qwen2 q/k/v have biases). */
+int af3_rope_table(void* stream, float* rope_cs, int B, int D, const int* pos_dev, const int* kv_start,
+                   const float* inv_freq);
+int af3_gemm_qkv_rope(void* stream, const void* x, int ldx, const void* w, int ldw, const void* bias, void* q_out, int ldo,
+                      int n_tok, int K, int H, int Hkv, int D, const float* rope_cs, void* k_cache, void* v_cache, int Tmax,
+                      const int* pos_dev, void* workspace, size_t workspace_bytes);
+
 /* Single-token attention over the KV cache (decode step; SDPA:40-104 with q_len = 1).  ctx_len is read from device
  * memory so the launch can live in a CUDA graph.  q at qkv (packed [B, (H+2Hkv)*D]); out [B, H*D]. */
 int af3_decode_attention(void* stream, const void* qkv, const void* k_cache, const void* v_cache, void* out,

@@ -43,6 +43,19 @@ def test_gemm_plain(ops, M, N, K):
     _close(out, ref, BF16_RTOL, 1e-3, f"gemm {M}x{N}x{K}")
 
 
+def test_gemm_unaligned_output_fallback(ops):
+    """Output pitch not a multiple of 8 elements: the smem/TMA-store epilogue is not applicable, the generic direct-store
+    epilogue (run-time flags) must still be exact."""
+    M, N, K = 130, 100, 64
+    x, w, b = _rand((M, K), 1.0, 17), _rand((N, K), 0.1, 18), _rand((N,), 0.5, 19)
+    out = ops.linear(x, w, b, gelu=True)
+    ref = torch.nn.functional.gelu((x.float() @ w.float().T + b.float()).to(bf16).float()).to(bf16)
+    _close(out, ref, BF16_RTOL, 2e-3, "unaligned N")
+    out32 = ops.linear(x[:20], w, b)  # few-token path with an odd feature count
+    ref32 = (x[:20].float() @ w.float().T + b.float()).to(bf16)
+    _close(out32, ref32, BF16_RTOL, 2e-3, "unaligned N (few tokens)")
+
+
 @pytest.mark.parametrize("M", [1, 7, 32, 33, 64])
 @pytest.mark.parametrize("N,K", [(256, 128), (3584, 512), (200, 64), (3584, 3584), (512, 4096)])  # the last three take the split-K path
 def test_gemm_swap_small_m(ops, M, N, K):
@@ -325,3 +338,20 @@ def test_logmel_vs_fp64(ops):
     err = np.abs(got - ref)
     assert got.shape == (2, 128, 3000)
     assert err.max() < 1e-4, err.max()
+
+
+def test_qkv_rope_fused_gemm_matches_unfused(ops):
+    """Decode-step fusion: q/k/v projection + RoPE + KV append in the GEMM epilogue == GEMM then af3_rope_kv_append."""
+    B, H, Hkv, D, K, Tmax, slot = 32, 28, 4, 128, 512, 64, 37
+    x, w, b = _rand((B, K), 1.0, 60), _rand(((H + 2 * Hkv) * D, K), 0.05, 61), _rand(((H + 2 * Hkv) * D,), 0.3, 62)
+    inv_freq = (1.0 / (1e6 ** (torch.arange(0, D, 2, dtype=torch.int64).float() / D))).cuda()
+    starts = torch.randint(0, 30, (B,), dtype=torch.int32).cuda()
+    pos = torch.tensor([slot], dtype=torch.int32, device="cuda")
+    kc1, vc1 = torch.zeros((B, Hkv, Tmax, D), device="cuda", dtype=bf16), torch.zeros((B, Hkv, Tmax, D), device="cuda", dtype=bf16)
+    kc2, vc2 = torch.zeros_like(kc1), torch.zeros_like(vc1)
+    qkv1 = ops.linear(x, w, b)
+    ops.rope_kv_append(qkv1, kc1, vc1, B=B, T=1, H=H, Hkv=Hkv, D=D, pos0=0, inv_freq=inv_freq, kv_start=starts, pos0_dev=pos)
+    cs = ops.rope_table(B, D, pos, starts, inv_freq)
+    qkv2 = ops.qkv_rope_linear(x, w, b, kc2, vc2, H=H, Hkv=Hkv, D=D, rope_cs=cs, pos_dev=pos)
+    assert torch.equal(qkv2[:, :H * D], qkv1[:, :H * D])
+    assert torch.equal(kc2, kc1) and torch.equal(vc2, vc1)
