@@ -10,7 +10,7 @@ from ._lib import AF3Error, lib_path, load as load_library  # noqa: F401
 
 
 def __getattr__(name):  # lazy: keep `import audio_flamingo_b200` light (torch/transformers only on first use)
-    if name in ("AudioFlamingo3ForConditionalGeneration", "AudioFlamingo3Encoder", "AudioFlamingo3MultiModalProjector",
+    if name in ("AudioFlamingo3ForConditionalGeneration", "MusicFlamingoForConditionalGeneration", "AudioFlamingo3Encoder", "AudioFlamingo3MultiModalProjector",
                 "Qwen2ForCausalLM", "AF3KVCache"):
         from . import modeling
 

@@ -15,6 +15,8 @@ struct RopeEpilogue {
 int gemm_bf16(cudaStream_t stream, const bf16* x, int ldx, const bf16* w, int ldw, void* out, int ldo, int n_tok,
               int n_feat, int K, int flags, const bf16* bias, const bf16* resid, int ld_res, int res_period,
               void* workspace, size_t workspace_bytes, const RopeEpilogue* rope);
+int rotary_time(cudaStream_t stream, bf16* x, const float* ts, const float* inv_freq, int W, int T, int dim, int n_freq,
+                float window_duration, float max_len);
 int rope_table(cudaStream_t stream, float* cs, int B, int D, const int* pos_dev, const int* kv_start, const float* inv_freq);
 size_t gemm_workspace_bytes();
 int logmel(cudaStream_t stream, const float* wave, int n_win, int n_samples, const float* hann, const float* table,
@@ -64,6 +66,11 @@ int af3_gemm_bf16_ws(void* stream, const void* x, int ldx, const void* w, int ld
                      void* workspace, size_t workspace_bytes) {
     return af3::gemm_bf16(S(stream), B16(x), ldx, B16(w), ldw, out, ldo, n_tok, n_feat, K, flags, B16(bias), B16(resid),
                           ld_res, res_period, workspace, workspace_bytes, nullptr);
+}
+
+int af3_rotary_time_emb(void* stream, void* x, const float* timestamps, const float* inv_freq, int W, int T, int dim, int n_freq,
+                        float window_duration, float max_len) {
+    return af3::rotary_time(S(stream), B16M(x), timestamps, inv_freq, W, T, dim, n_freq, window_duration, max_len);
 }
 
 int af3_rope_table(void* stream, float* cs, int B, int D, const int* pos_dev, const int* kv_start, const float* inv_freq) {

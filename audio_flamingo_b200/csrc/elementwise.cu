@@ -423,6 +423,53 @@ int rope_kv_append(cudaStream_t stream, bf16* qkv, bf16* k_cache, bf16* v_cache,
     return 0;
 }
 
+// Music Flamingo rotary TIME embedding on the AF-Whisper output ([O] transformers/models/musicflamingo/
+// modular_musicflamingo.py:167-227: rotate_half on interleaved pairs, MusicFlamingoRotaryEmbedding.forward, and
+// apply_rotary_time_emb which computes in fp64).  x bf16 [W*T, dim] in place; the first 4*n_freq features are rotated:
+//   features [0, 2 n_freq)        : window axis, freq = (round(ts[w,0] / window_duration) / max_len) * inv_freq[j/2]
+//   features [2 n_freq, 4 n_freq) : time axis,   freq = ((t / max_len) * 2 pi) * inv_freq[(j - 2 n_freq)/2]
+// each multiplied by angle = -ts[w,t] * 2 * pi, all in fp32 exactly in the reference's operation order; cos/sin in fp32,
+// the rotation itself in fp64, one rounding back to bf16.  One thread per (row, pair).
+__global__ void __launch_bounds__(256)
+rotary_time_kernel(bf16* __restrict__ x, const float* __restrict__ ts, const float* __restrict__ inv_freq, int W, int T, int dim,
+                   int n_freq, float window_duration, float max_len) {
+    const long long total = static_cast<long long>(W) * T * 2 * n_freq;
+    const float two_pi = static_cast<float>(2.0 * 3.141592653589793);
+    const float pi_f = static_cast<float>(3.141592653589793);
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int p = static_cast<int>(i % (2 * n_freq));  // pair index: features 2p, 2p+1
+        const long long row = i / (2 * n_freq);
+        const int t = static_cast<int>(row % T), w = static_cast<int>(row / T);
+        float freq;
+        if (p < n_freq) {
+            const float wpos = rintf(ts[static_cast<size_t>(w) * T] / window_duration) / max_len;
+            freq = wpos * inv_freq[p];
+        } else {
+            const float pos = (static_cast<float>(t) / max_len) * two_pi;
+            freq = pos * inv_freq[p - n_freq];
+        }
+        const float angle = ((-ts[row]) * 2.0f) * pi_f;
+        const float f = freq * angle;
+        const double c = static_cast<double>(cosf(f)), s = static_cast<double>(sinf(f));
+        bf16* px = x + row * dim + 2 * p;
+        const double x0 = static_cast<double>(__bfloat162float(px[0])), x1 = static_cast<double>(__bfloat162float(px[1]));
+        px[0] = __double2bfloat16(x0 * c + (-x1) * s);
+        px[1] = __double2bfloat16(x1 * c + x0 * s);
+    }
+}
+
+int rotary_time(cudaStream_t stream, bf16* x, const float* ts, const float* inv_freq, int W, int T, int dim, int n_freq,
+                float window_duration, float max_len) {
+    AF3_REQUIRE(4 * n_freq <= dim && n_freq > 0, "rotary_time: rotary width exceeds the feature dim");
+    const long long total = static_cast<long long>(W) * T * 2 * n_freq;
+    if (total <= 0) return 0;
+    const int grid = static_cast<int>(((total + 255) / 256) < 148ll * 16 ? ((total + 255) / 256) : 148ll * 16);
+    rotary_time_kernel<<<grid, 256, 0, stream>>>(x, ts, inv_freq, W, T, dim, n_freq, window_duration, max_len);
+    AF3_CHECK_LAUNCH();
+    return 0;
+}
+
 // cos/sin table of ONE decode step for the RoPE-fused q/k/v projection epilogue: cs[b][i] = (bf16(cos), bf16(sin)) of
 // inv_freq[i] * position(b), position = slot - kv_start[b] (Q2M:100-113; identical for all layers of the step).
 __global__ void rope_table_kernel(float2* __restrict__ cs, int B, int half, const int* __restrict__ pos_dev,

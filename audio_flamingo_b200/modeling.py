@@ -410,9 +410,10 @@ class AudioFlamingo3ForConditionalGeneration(nn.Module):
 
     # ---- audio branch
     @torch.no_grad()
-    def get_audio_features(self, input_features, input_features_mask, **kwargs):
+    def get_audio_features(self, input_features, input_features_mask, input_ids=None, **kwargs):
         """[O] AF3M:447-475: tower -> projector -> keep the first post_len frames of every window."""
         enc, W, Tp = self.audio_tower._encode(input_features, input_features_mask)
+        enc = self._post_encoder(enc, W, Tp, input_features_mask, input_ids)
         emb = self.multi_modal_projector(enc)                                   # [W*Tp, text_hidden]
         lens = input_features_mask.sum(-1).to(torch.long)
         _, post = self.audio_tower._get_feat_extract_output_lengths(lens)
@@ -421,8 +422,13 @@ class AudioFlamingo3ForConditionalGeneration(nn.Module):
         out.pooler_output = emb.view(W, Tp, -1)[valid]
         return out
 
-    def _audio_embeds_raw(self, input_features, input_features_mask):
+    def _post_encoder(self, enc, W, Tp, input_features_mask, input_ids):
+        """Hook between the audio tower and the projector (identity for AF3; Music Flamingo rotates here)."""
+        return enc
+
+    def _audio_embeds_raw(self, input_features, input_features_mask, input_ids=None):
         enc, W, Tp = self.audio_tower._encode(input_features, input_features_mask)
+        enc = self._post_encoder(enc, W, Tp, input_features_mask, input_ids)
         emb = self.multi_modal_projector(enc)
         lens = input_features_mask.sum(-1).to(torch.int32)
         post = (((lens - 1) // 2 + 1) - 2) // 2 + 1
@@ -447,7 +453,7 @@ class AudioFlamingo3ForConditionalGeneration(nn.Module):
         ids = input_ids.to(dev).reshape(-1).contiguous()
         table = self.language_model.model.embed_tokens.weight
         if input_features is not None:
-            emb, W, Tp, post = self._audio_embeds_raw(input_features.to(dev), input_features_mask.to(dev))
+            emb, W, Tp, post = self._audio_embeds_raw(input_features.to(dev), input_features_mask.to(dev), input_ids.to(dev))
             x, counts = ops.embed_scatter(ids, table, self.config.audio_token_id, emb, W, Tp, post)
             n_tok, n_feat = counts.tolist()
             if n_tok != n_feat:  # masked_scatter would fail the same way (AF3M:564)
@@ -588,3 +594,50 @@ class AudioFlamingo3ForConditionalGeneration(nn.Module):
             return state["out"]
 
         return step
+
+
+class MusicFlamingoForConditionalGeneration(AudioFlamingo3ForConditionalGeneration):
+    """Music Flamingo = the AF3 path + a rotary TIME embedding on the audio-tower output.
+    Mirrors [O] transformers/models/musicflamingo/modular_musicflamingo.py:245-322 (same parameters / state_dict keys
+    as AF3; the rotary buffers are non-persistent there and are recomputed here)."""
+
+    def __init__(self, config):
+        super().__init__(config)
+        rp = config.rope_parameters
+        if rp.get("rope_type", "default") != "default":
+            raise AF3Error("only default rope parameters are implemented for the rotary time embedding")
+        base = rp["rope_theta"]
+        head_dim = _cfg_get(config, "head_dim", None) or config.audio_config.hidden_size
+        dim = int(head_dim * rp.get("partial_rotary_factor", 1.0))
+        # MoonshineRotaryEmbedding.compute_default_rope_parameters, evaluated on the CPU like the reference
+        self._mf_inv_freq_cpu = 1.0 / (base ** (torch.arange(0, dim, 2, dtype=torch.int64).to(dtype=torch.float) / dim))
+        self._mf_inv_freq = None
+        self._mf_max_len = float(config.max_position_embeddings)
+        self._mf_frame_step = config.audio_frame_step
+
+    def _build_audio_timestamps(self, input_ids, post_lengths, max_post_length):
+        """Seconds of every encoder output row; index arithmetic of [O] modular_musicflamingo.py:250-285 on the device."""
+        audio_token_mask = input_ids == self.config.audio_token_id
+        diff = torch.diff(torch.nn.functional.pad(audio_token_mask.int(), (1, 1), value=0), dim=1)
+        _, starts = torch.where(diff == 1)
+        _, ends = torch.where(diff == -1)
+        sample_lengths = (ends - starts).to(torch.long)
+        step = self._mf_frame_step * 4
+        frame_offsets = torch.arange(max_post_length, device=post_lengths.device, dtype=torch.float32) * step
+        cumsum_post = torch.cat([torch.zeros(1, device=post_lengths.device), torch.cumsum(post_lengths, dim=0)[:-1]])
+        cumsum_samples = torch.cumsum(sample_lengths, dim=0)
+        sample_indices = torch.searchsorted(cumsum_samples, cumsum_post, right=True)
+        sample_start_rows = torch.searchsorted(sample_indices, torch.arange(sample_lengths.shape[0], device=post_lengths.device))
+        window_indices = torch.arange(post_lengths.shape[0], device=post_lengths.device) - sample_start_rows[sample_indices]
+        return window_indices.unsqueeze(1) * max_post_length * step + frame_offsets
+
+    def _post_encoder(self, enc, W, Tp, input_features_mask, input_ids):
+        if input_ids is None:
+            raise AF3Error("Music Flamingo needs input_ids to place the audio windows in time (get_audio_features(..., input_ids=))")
+        if self._mf_inv_freq is None or self._mf_inv_freq.device != enc.device:
+            self._mf_inv_freq = self._mf_inv_freq_cpu.to(enc.device)
+        lens = input_features_mask.sum(-1).to(torch.long)
+        _, post = self.audio_tower._get_feat_extract_output_lengths(lens)
+        ts = self._build_audio_timestamps(input_ids.to(enc.device), post, Tp).to(torch.float32).contiguous()
+        window_duration = self._mf_frame_step * 4 * Tp
+        return ops.rotary_time_emb(enc, ts, self._mf_inv_freq, W, Tp, window_duration, self._mf_max_len)

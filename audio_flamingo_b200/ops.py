@@ -256,6 +256,17 @@ def rope_kv_append(qkv, k_cache, v_cache, *, B, T, H, Hkv, D, pos0, inv_freq, kv
     _count(1)
 
 
+def rotary_time_emb(x, timestamps, inv_freq, W, T, window_duration, max_len):
+    """Music Flamingo rotary time embedding, in place on x [W*T, dim] bf16."""
+    lib = _lib.load()
+    _req(x, bf16, "x"), _req(timestamps, torch.float32, "timestamps"), _req(inv_freq, torch.float32, "inv_freq")
+    with _Timed(("rotary_time", W * T, x.shape[1], 0, 0)):
+        check(lib.af3_rotary_time_emb(stream_ptr(), ptr(x), ptr(timestamps), ptr(inv_freq), W, T, x.shape[1], inv_freq.numel(),
+                                      float(window_duration), float(max_len)), "af3_rotary_time_emb")
+    _count(1)
+    return x
+
+
 def rope_table(B, D, pos_dev, kv_start, inv_freq, out=None):
     """(cos, sin) of this decode step for every sequence: fp32 [B, D/2, 2] (shared by all layers)."""
     lib = _lib.load()
@@ -290,19 +301,19 @@ def qkv_rope_linear(x, w, bias, k_cache, v_cache, *, H, Hkv, D, rope_cs, pos_dev
 def decode_attention(qkv, k_cache, v_cache, out, scratch, *, B, H, Hkv, D, ctx_len, kv_start, scale):
     lib = _lib.load()
     Tmax = k_cache.shape[2]
-    with _Timed(("decode_attention", B, H, Tmax, 0)):  # one launch (the last chunk CTA merges the partials)
+    with _Timed(("decode_attention", B, H, Tmax, 0)):
         check(
             lib.af3_decode_attention(stream_ptr(), ptr(qkv), ptr(k_cache), ptr(v_cache), ptr(out), ptr(scratch), B, H, Hkv, D,
                                      Tmax, ptr(ctx_len), ptr(kv_start), float(scale)),
             "af3_decode_attention",
         )
-    _count(1)
+    _count(2)
     return out
 
 
 def decode_attention_scratch(B, H, D, Tmax, device):
     n = _lib.load().af3_decode_attention_scratch_bytes(B, H, D, Tmax)
-    return torch.zeros(((n + 3) // 4,), device=device, dtype=torch.float32)  # zero: holds the arrival counters
+    return torch.empty(((n + 3) // 4,), device=device, dtype=torch.float32)
 
 
 # ----------------------------------------------------------------------------------------------- glue

@@ -98,6 +98,12 @@ int af3_attention(void* stream, const void* q, int ldq, const void* k, const voi
 int af3_rope_kv_append(void* stream, void* qkv, void* k_cache, void* v_cache, int B, int T, int H, int Hkv, int D,
                        int Tmax, int pos0, const int* pos0_dev, const int* kv_start, const float* inv_freq);
 
+/* Music Flamingo rotary time embedding ([O] musicflamingo/modular_musicflamingo.py:167-227) applied in place
+ * to the AF-Whisper output x [W*T, dim] bf16: first 4*n_freq features rotated (window axis then time axis, interleaved
+ * pairs) by angles built from timestamps [W, T] (seconds, fp32) and inv_freq [n_freq]; fp64 rotation, bf16 result. */
+int af3_rotary_time_emb(void* stream, void* x, const float* timestamps, const float* inv_freq, int W, int T, int dim,
+                        int n_freq, float window_duration, float max_len);
+
 /* Decode-step fusion of the q/k/v projection with RoPE and the KV append (Q2M:199-215 + CACHE:119-120 in one kernel):
  * out rows get the ROTATED query heads (columns [0, H*D)); rotated keys and the values go straight into the caches at
  * slot *pos_dev.  rope_cs [n_tok][D/2][2] fp32 from af3_rope_table (once per step, shared by all layers).

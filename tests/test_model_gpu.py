@@ -162,3 +162,55 @@ def test_pdl_decode_is_bit_identical(O, monkeypatch):
     g0, l0 = ours.generate(**kw)
     assert torch.equal(g1, g0) and torch.equal(l1, l0)
     assert torch.equal(g1e, g0) and torch.equal(l1e, l0)
+
+
+def test_music_flamingo_rotary_time_embedding(O):
+    """Music Flamingo = AF3 + rotary time embedding on the audio-tower output.  Audio features and logits
+    vs the HF MusicFlamingoForConditionalGeneration (same seeded weights) in fp32 and in bf16 on the same GPU; a 45 s
+    clip exercises the window axis (window index 1 -> non-zero window rotation)."""
+    from transformers import MusicFlamingoConfig, MusicFlamingoForConditionalGeneration as HFMusic
+
+    from audio_flamingo_b200 import AF3FeatureExtractor, MusicFlamingoForConditionalGeneration
+    from audio_flamingo_b200.processing import expand_audio_spans, left_pad, split_windows, tokens_per_sample
+
+    p = O.TINY
+    text = dict(p["text"])
+    theta = text.pop("rope_theta")
+    cfg = MusicFlamingoConfig(audio_config=dict(p["audio"], model_type="musicflamingo_encoder"),
+                              text_config=dict(text, rope_parameters={"rope_type": "default", "rope_theta": theta}),
+                              audio_token_id=p["audio_token_id"], audio_bos_token_id=2045, audio_eos_token_id=2046,
+                              rope_parameters={"rope_type": "default", "rope_theta": 1200, "partial_rotary_factor": 0.2})
+    assert cfg.max_position_embeddings == 1200
+    torch.manual_seed(11)
+    ref32 = HFMusic(cfg).eval()
+    with torch.no_grad():
+        ref32.language_model.lm_head.weight.mul_(8.0)
+    clips = O.synth_waveforms(2, [45.0, 8.0], seed=31)
+    chunks, per = split_windows(clips)
+    fe = AF3FeatureExtractor("cuda")
+    fo = fe(chunks, sampling_rate=16000)
+    frames = fo["attention_mask"].sum(-1).cpu().tolist()
+    n0, n1 = tokens_per_sample(frames, per)
+    rs = np.random.RandomState(5)
+    aid, V = cfg.audio_token_id, cfg.text_config.vocab_size
+    t = lambda n: rs.randint(1, 2000, size=n).tolist()
+    ids, am = left_pad([expand_audio_spans(t(4) + [aid] + t(6), aid, [n0]), expand_audio_spans(t(3) + [aid] + t(9), aid, [n1])])
+    feats_ref, fmask_ref = O.hf_features(chunks)
+    ours = MusicFlamingoForConditionalGeneration.from_reference(ref32, device="cuda")
+    with torch.no_grad():
+        a32 = ref32.get_audio_features(feats_ref, fmask_ref, input_ids=ids)
+        l32 = ref32(input_ids=ids, attention_mask=am, input_features=feats_ref, input_features_mask=fmask_ref).logits
+    ao = ours.get_audio_features(fo["input_features"], fo["input_features_mask"], input_ids=ids.cuda())
+    lo = ours(input_ids=ids.cuda(), attention_mask=am.cuda(), input_features=fo["input_features"],
+              input_features_mask=fo["input_features_mask"]).logits.float().cpu()
+    ea = (ao.pooler_output.float().cpu() - a32.pooler_output).abs().max().item()
+    assert ea < 0.03 * a32.pooler_output.abs().max().item(), ea
+    v = am.bool()
+    assert (lo - l32)[v].abs().max().item() < 0.06 * l32[v].std().item()
+    # the rotation must actually matter: AF3 (no rotation) on the same weights differs visibly
+    from audio_flamingo_b200 import AudioFlamingo3ForConditionalGeneration
+
+    plain = AudioFlamingo3ForConditionalGeneration(cfg)
+    plain.load_reference_state_dict(ref32.state_dict(), device="cuda")
+    ap = plain.get_audio_features(fo["input_features"], fo["input_features_mask"]).pooler_output.float().cpu()
+    assert (ap - a32.pooler_output).abs().max().item() > 5 * ea
