@@ -9,7 +9,8 @@
 //     O^T[dim, head] = V_tile^T[dim, key] . P^T[key, head]   tcgen05.mma 128x16x16 x 8,  A = V tile read MN-major
 // so the K and V tiles stream HBM -> smem by TMA (2 x 32 KB in flight per CTA, 3 CTAs/SM) and never pass through
 // registers; the softmax over the chunk is a cross-lane reduction of 16 columns (thread = key = TMEM lane).
-// B*Hkv*ceil(Tmax/128) CTAs cover the GPU; a second kernel merges the chunk partials (log-sum-exp combine).
+// B*Hkv*ceil(Tmax/128) CTAs cover the GPU; the last-arriving chunk CTA of a (sequence, KV head) merges the chunk partials
+// (log-sum-exp combine) -- no separate combine kernel.
 // ctx_len lives in device memory so the launch parameters are step-invariant (CUDA-graph replay); chunks beyond the
 // live context exit immediately.  Cache rows beyond the live context must hold finite values (the cache is
 // zero-initialised): they are multiplied by P = 0.
@@ -35,10 +36,61 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         : "memory");
 }
 
+// Merge of the chunk partials of one (sequence, KV head), executed by the last-arriving chunk CTA.  Partial layout
+// [b][h][split][D + 4] = (unnormalised o[D] relative to the chunk max, chunk max (log2 domain), chunk sum, pad).
+// Work item = (head, 4 output dims): G * 32 items over the CTA's threads; the loads of all splits of an item are
+// independent (two dependent rounds in total: maxima, then sums + outputs).  Chunks outside [start, ctx) never wrote
+// theirs and are skipped by index.  Resets the arrival counter.
+__device__ __forceinline__ void combine_heads(const float* __restrict__ part, bf16* __restrict__ out, int* counters, int b, int hk,
+                                              int G, int H, int Hkv, int nsplit, int ctx, int start) {
+    constexpr int D = DA_D, ST = D + 4, SB = 8;  // splits handled per unrolled block
+    __threadfence();
+    const int s_lo = start / DA_CHUNK, s_hi = (ctx + DA_CHUNK - 1) / DA_CHUNK;  // chunks that hold live keys
+    for (int item = threadIdx.x; item < G * (D / 4); item += blockDim.x) {
+        const int g = item / (D / 4), dq = item % (D / 4);
+        const int h = hk * G + g;
+        const float* src = part + (static_cast<size_t>(b) * H + h) * nsplit * ST;
+        float m = -INFINITY;
+        for (int s0 = s_lo; s0 < s_hi; s0 += SB) {
+            float ms[SB];
+#pragma unroll
+            for (int j = 0; j < SB; ++j) ms[j] = (s0 + j < s_hi) ? __ldcg(src + (s0 + j) * ST + D) : -INFINITY;
+#pragma unroll
+            for (int j = 0; j < SB; ++j) m = fmaxf(m, ms[j]);
+        }
+        float l = 0.f;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s0 = s_lo; s0 < s_hi; s0 += SB) {
+            float2 ml[SB];
+            float4 ov[SB];
+#pragma unroll
+            for (int j = 0; j < SB; ++j) {
+                const bool ok = s0 + j < s_hi;
+                ml[j] = ok ? __ldcg(reinterpret_cast<const float2*>(src + (s0 + j) * ST + D)) : make_float2(-INFINITY, 0.f);
+                ov[j] = ok ? __ldcg(reinterpret_cast<const float4*>(src + (s0 + j) * ST + dq * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < SB; ++j) {
+                const float w = (ml[j].x == -INFINITY) ? 0.f : exp2f(ml[j].x - m);
+                l += w * ml[j].y;
+                o.x += w * ov[j].x;
+                o.y += w * ov[j].y;
+                o.z += w * ov[j].z;
+                o.w += w * ov[j].w;
+            }
+        }
+        const float inv = l > 0.f ? 1.f / l : 0.f;
+        bf16* dst = out + (static_cast<size_t>(b) * H + h) * D + dq * 4;
+        *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(o.x * inv, o.y * inv), pack_bf16x2(o.z * inv, o.w * inv));
+    }
+    if (threadIdx.x == 0) counters[b * Hkv + hk] = 0;
+}
+
 __global__ void __launch_bounds__(DA_THREADS)
 decode_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
-                   const __grid_constant__ CUtensorMap map_v, float* __restrict__ part, int H, int Hkv, int nsplit,
-                   const int* __restrict__ ctx_len_p, const int* __restrict__ kv_start, float scale_log2) {
+                   const __grid_constant__ CUtensorMap map_v, float* __restrict__ part, bf16* __restrict__ out,
+                   int* __restrict__ counters, int H, int Hkv, int nsplit, const int* __restrict__ ctx_len_p,
+                   const int* __restrict__ kv_start, float scale_log2) {
     constexpr int D = DA_D;
     const int G = H / Hkv;
     const int b = blockIdx.x, hk = blockIdx.y, sp = blockIdx.z;
@@ -49,13 +101,12 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     const int start = kv_start ? kv_start[b] : 0;
     const int j0 = sp * DA_CHUNK;
     const int j_beg = max(j0, start), j_end = min(j0 + DA_CHUNK, ctx);
-    float* pbase = part + ((static_cast<size_t>(b) * H + hk * G) * nsplit + sp) * (D + 2);
-    if (j_beg >= j_end) {  // chunk entirely outside the live context: publish an empty partial
-        if (tid < G) {
-            float* dst = pbase + static_cast<size_t>(tid) * nsplit * (D + 2);
-            dst[D] = -INFINITY;
-            dst[D + 1] = 0.f;
-        }
+    float* pbase = part + ((static_cast<size_t>(b) * H + hk * G) * nsplit + sp) * (D + 4);
+    if (j_beg >= j_end) {  // chunk entirely outside the live context: it only counts as arrived
+        __shared__ int last_flag;
+        if (tid == 0) last_flag = (atomicAdd(counters + b * Hkv + hk, 1) == nsplit - 1);
+        __syncthreads();
+        if (last_flag) combine_heads(part, out, counters, b, hk, G, H, Hkv, nsplit, ctx, start);
         return;
     }
     extern __shared__ uint8_t smem_raw[];
@@ -173,7 +224,7 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 #pragma unroll
         for (int g = 0; g < DA_NH; ++g) {
             if (g < G) {
-                float* dst = pbase + static_cast<size_t>(g) * nsplit * (D + 2);
+                float* dst = pbase + static_cast<size_t>(g) * nsplit * (D + 4);
                 dst[tid] = __uint_as_float(ov[g]);
                 if (tid == 0) {
                     dst[D] = m[g];
@@ -183,35 +234,26 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         }
     }
     tc_fence_before();
+    __threadfence();  // partials visible before this chunk is counted
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_S, 32);
-}
-
-// partial layout: [b][h][split][D + 2] = (unnormalised o[D] relative to the chunk max, chunk max (log2 domain), chunk sum)
-template <int D>
-__global__ void __launch_bounds__(D)
-decode_attn_combine(const float* __restrict__ part, bf16* __restrict__ out, int H, int nsplit) {
-    const int b = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
-    pdl_launch_dependents();
-    pdl_wait();
-    const float* src = part + (static_cast<size_t>(b) * H + h) * nsplit * (D + 2);
-    float m = -INFINITY;
-    for (int s = 0; s < nsplit; ++s) m = fmaxf(m, src[s * (D + 2) + D]);
-    float l = 0.f, o = 0.f;
-    for (int s = 0; s < nsplit; ++s) {
-        const float ms = src[s * (D + 2) + D];
-        if (ms == -INFINITY) continue;  // empty chunk (its o slots were never written)
-        const float w = exp2f(ms - m);
-        l += w * src[s * (D + 2) + D + 1];
-        o += w * src[s * (D + 2) + tid];
-    }
-    out[(static_cast<size_t>(b) * H + h) * D + tid] = __float2bfloat16_rn(l > 0.f ? o / l : 0.f);
+    // ---- the last-arriving chunk CTA of this (sequence, KV head) merges all chunk partials (log-sum-exp combine):
+    //      replaces a separate combine kernel per layer
+    int* flag = reinterpret_cast<int*>(red);
+    if (tid == 0) *flag = (atomicAdd(counters + b * Hkv + hk, 1) == nsplit - 1);
+    __syncthreads();
+    if (*flag) combine_heads(part, out, counters, b, hk, G, H, Hkv, nsplit, ctx, start);
 }
 
 static int n_splits(int Tmax) { return ceil_div(Tmax, DA_CHUNK); }
 
+// scratch = chunk partials + one arrival counter per (sequence, KV head); the counters must be ZERO on first use (the kernel
+// leaves them zero)
+static size_t partial_bytes(int B, int H, int D, int Tmax) {
+    return (static_cast<size_t>(B) * H * n_splits(Tmax) * (D + 4) * sizeof(float) + 255) & ~static_cast<size_t>(255);
+}
 size_t decode_attention_scratch_bytes(int B, int H, int D, int Tmax) {
-    return static_cast<size_t>(B) * H * n_splits(Tmax) * (D + 2) * sizeof(float);
+    return partial_bytes(B, H, D, Tmax) + static_cast<size_t>(B) * H * sizeof(int);
 }
 
 int decode_attention(cudaStream_t stream, const bf16* qkv, const bf16* k_cache, const bf16* v_cache, bf16* out,
@@ -237,10 +279,9 @@ int decode_attention(cudaStream_t stream, const bf16* qkv, const bf16* k_cache, 
                              DA_CHUNK, 1))
         return e;
     dim3 grid(B, Hkv, ns);
-    AF3_CHECK_CUDA(launch_kernel(decode_attn_kernel, grid, dim3(DA_THREADS), DA_SMEM, stream, mq, mk, mv, scratch, H, Hkv, ns,
-                                 ctx_len, kv_start, scale * 1.4426950408889634f));
-    dim3 g2(B, H);
-    AF3_CHECK_CUDA(launch_kernel(decode_attn_combine<128>, g2, dim3(128), 0, stream, static_cast<const float*>(scratch), out, H, ns));
+    int* counters = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(scratch) + partial_bytes(B, H, D, Tmax));
+    AF3_CHECK_CUDA(launch_kernel(decode_attn_kernel, grid, dim3(DA_THREADS), DA_SMEM, stream, mq, mk, mv, scratch, out, counters, H,
+                                 Hkv, ns, ctx_len, kv_start, scale * 1.4426950408889634f));
     return 0;
 }
 

@@ -97,8 +97,11 @@ __device__ __forceinline__ float epi_swiglu(float g, float u) {
 
 // EPI >= 0: epilogue flags fixed at compile time (no per-element branches, full ILP across the 32-column chunk);
 // EPI < 0: generic instantiation reading a.flags at run time (odd layouts / unusual flag mixes).
-template <int BN, int NA, int STAGES, bool SWAP, int EPI>
-__global__ void __launch_bounds__(192, 1)
+// EW = epilogue warps (4 or 8).  With 8 (normal mode, epilogues without a TMA-prefetched residual) two warps share each
+// TMEM lane quarter and split the tile's 64-column groups between them: twice the issue slots for epilogue math, which
+// is what bounds short-K GEMMs with expensive epilogues (K = 1280 + GELU: erff per element).
+template <int BN, int NA, int STAGES, bool SWAP, int EPI, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_c,
             const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res, const GemmArgs a) {
     using Cfg = GemmCfg<BN, NA, STAGES, SWAP>;
@@ -124,7 +127,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull[i], 1);
-            mbar_init(&tempty[i], 128);
+            mbar_init(&tempty[i], 32 * EW);
         }
         for (int i = 0; i < 8; ++i) mbar_init(&rbar[i], 1);
         if (a.tma_epi) {
@@ -239,6 +242,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
         __syncwarp();
     } else {
         const int q = warp & 3;  // TMEM lane quarter this warp may access
+        [[maybe_unused]] const int ehalf = (EW == 8) ? ((warp - 2) >> 2) : 0;  // which half of the column groups (EW == 8)
         const int row_in_tile = q * 32 + lane;
         const int flags = (EPI >= 0) ? EPI : a.flags;
         pdl_wait();  // residual reads / output writes / split-K workspace are ordered after every earlier kernel
@@ -272,9 +276,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
                 if (a.tma_epi) {
                     // ---- smem-staged epilogue: per warp, 64 output columns at a time -> [32 rows x 128 B] swizzled slab -> TMA store
                     const int n_groups = (swiglu ? BN / 2 : BN) / 64;
+                    // EW == 8: this warp owns half of the groups and ONE staging buffer (index ehalf); EW == 4: all groups,
+                    // two alternating buffers
+                    const int g_lo = (EW == 8) ? ehalf * (n_groups / 2) : 0;
+                    const int g_hi = (EW == 8) ? g_lo + n_groups / 2 : n_groups;
 #pragma unroll 1
-                    for (int gi = 0; gi < n_groups; ++gi) {
-                        const int buf = egrp & 1;
+                    for (int gi = g_lo; gi < g_hi; ++gi) {
+                        const int buf = (EW == 8) ? ehalf : (egrp & 1);
                         uint8_t* sbuf = epi_stage + (q * 2 + buf) * 4096;
                         if (out_col_base + gi * 64 >= a.n_feat) break;  // fully out-of-range group (warp-uniform)
                         if (lane == 0) {
@@ -285,6 +293,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
                                     tma_load_2d(epi_stage + (q * 2 + (buf ^ 1)) * 4096, &map_res, &rbar[q * 2 + (buf ^ 1)],
                                                 out_col_base + (gi + 1) * 64, row0);
                                 }
+                            } else if (EW == 8) {
+                                bulk_wait_read<0>();  // single buffer per warp: the previous store has drained it
                             } else {
                                 bulk_wait_read<1>();  // the store that last used THIS buffer has drained it
                             }
@@ -644,11 +654,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
     if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
-template <int BN, int NA, int STAGES, bool SWAP, int EPI>
+template <int BN, int NA, int STAGES, bool SWAP, int EPI, int EW = 4>
 static int launch_epi(const CUtensorMap& mr, const CUtensorMap& mc, const CUtensorMap& mo, const CUtensorMap& mres,
                   const GemmArgs& a, cudaStream_t stream) {
     using Cfg = GemmCfg<BN, NA, STAGES, SWAP>;
-    auto kern = gemm_kernel<BN, NA, STAGES, SWAP, EPI>;
+    auto kern = gemm_kernel<BN, NA, STAGES, SWAP, EPI, EW>;
     static bool configured = false;
     if (!configured) {
         AF3_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -656,7 +666,7 @@ static int launch_epi(const CUtensorMap& mr, const CUtensorMap& mc, const CUtens
     }
     const int tiles = a.num_r_tiles * a.num_c_tiles * (SWAP && a.k_splits > 1 ? a.k_splits : 1);
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    AF3_CHECK_CUDA(launch_kernel(kern, dim3(grid), dim3(192), Cfg::SMEM_BYTES, stream, mr, mc, mo, mres, a));
+    AF3_CHECK_CUDA(launch_kernel(kern, dim3(grid), dim3(64 + 32 * EW), Cfg::SMEM_BYTES, stream, mr, mc, mo, mres, a));
     return 0;
 }
 
@@ -669,6 +679,23 @@ static int launch(const CUtensorMap& mr, const CUtensorMap& mc, const CUtensorMa
 #define AF3_EPI_CASE(F) \
     case (F):           \
         return launch_epi<BN, NA, STAGES, SWAP, (F)>(mr, mc, mo, mres, a, stream);
+    if constexpr (!SWAP) {
+        // 8 epilogue warps where the epilogue (not the MMA) bounds the tile: TMA-store path without a TMA residual
+        if (a.tma_epi && !((a.flags & EPI_RESID) && a.res_period == 0)) {
+            switch (a.flags) {
+                case 0:
+                    return launch_epi<BN, NA, STAGES, SWAP, 0, 8>(mr, mc, mo, mres, a, stream);
+                case EPI_BIAS:
+                    return launch_epi<BN, NA, STAGES, SWAP, EPI_BIAS, 8>(mr, mc, mo, mres, a, stream);
+                case EPI_BIAS | EPI_GELU:
+                    return launch_epi<BN, NA, STAGES, SWAP, EPI_BIAS | EPI_GELU, 8>(mr, mc, mo, mres, a, stream);
+                case EPI_BIAS | EPI_GELU | EPI_RESID:
+                    return launch_epi<BN, NA, STAGES, SWAP, EPI_BIAS | EPI_GELU | EPI_RESID, 8>(mr, mc, mo, mres, a, stream);
+                default:
+                    break;
+            }
+        }
+    }
     if (SWAP || a.tma_epi) {
         switch (a.flags) {
             AF3_EPI_CASE(0)

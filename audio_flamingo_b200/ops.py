@@ -307,13 +307,13 @@ def decode_attention(qkv, k_cache, v_cache, out, scratch, *, B, H, Hkv, D, ctx_l
                                      Tmax, ptr(ctx_len), ptr(kv_start), float(scale)),
             "af3_decode_attention",
         )
-    _count(2)
+    _count(1)
     return out
 
 
 def decode_attention_scratch(B, H, D, Tmax, device):
     n = _lib.load().af3_decode_attention_scratch_bytes(B, H, D, Tmax)
-    return torch.empty(((n + 3) // 4,), device=device, dtype=torch.float32)
+    return torch.zeros(((n + 3) // 4,), device=device, dtype=torch.float32)  # zero: holds the arrival counters
 
 
 # ----------------------------------------------------------------------------------------------- glue
