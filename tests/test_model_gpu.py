@@ -214,3 +214,40 @@ def test_music_flamingo_rotary_time_embedding(O):
     plain.load_reference_state_dict(ref32.state_dict(), device="cuda")
     ap = plain.get_audio_features(fo["input_features"], fo["input_features_mask"]).pooler_output.float().cpu()
     assert (ap - a32.pooler_output).abs().max().item() > 5 * ea
+
+
+def test_long_audio_five_windows(O):
+    """SURVEY 8-f.2: long audio = more 30 s windows per sample (here 140 s -> 5 windows -> 3 502 audio tokens in one prompt);
+    prefill attention runs 28 query tiles x up to 28 key tiles per head with left padding on the shorter row."""
+    from audio_flamingo_b200 import AF3FeatureExtractor, AudioFlamingo3ForConditionalGeneration
+    from audio_flamingo_b200.processing import expand_audio_spans, left_pad, split_windows, tokens_per_sample
+
+    ref32 = O.hf_model("tiny", seed=0, sharpen=8.0)
+    cfg = ref32.config
+    aid, V = cfg.audio_token_id, cfg.text_config.vocab_size
+    clips = O.synth_waveforms(2, [140.0, 33.0], seed=41)
+    chunks, per = split_windows(clips)
+    assert per == [5, 2]
+    fe = AF3FeatureExtractor("cuda")
+    fo = fe(chunks, sampling_rate=16000)
+    n0, n1 = tokens_per_sample(fo["attention_mask"].sum(-1).cpu().tolist(), per)
+    assert n0 == 3500 and n1 == 825
+    rs = np.random.RandomState(7)
+    t = lambda n: rs.randint(1, V - 2, size=n).tolist()
+    ids, am = left_pad([expand_audio_spans(t(5) + [aid] + t(20), aid, [n0]), expand_audio_spans(t(5) + [aid] + t(20), aid, [n1])])
+    feats_ref, fmask_ref = O.hf_features(chunks)
+    ours = AudioFlamingo3ForConditionalGeneration.from_reference(ref32, device="cuda")
+    with torch.no_grad():
+        l32 = ref32(input_ids=ids, attention_mask=am, input_features=feats_ref, input_features_mask=fmask_ref, logits_to_keep=1).logits
+        g_ref = ref32.generate(input_ids=ids, attention_mask=am, input_features=feats_ref, input_features_mask=fmask_ref,
+                               max_new_tokens=4, do_sample=False)
+    out = ours(input_ids=ids.cuda(), attention_mask=am.cuda(), input_features=fo["input_features"],
+               input_features_mask=fo["input_features_mask"], logits_to_keep=1)
+    lo = out.logits.float().cpu()
+    assert lo.shape == l32.shape
+    assert (lo - l32).abs().max().item() < 0.08 * l32.std().item()
+    g = ours.generate(input_ids=ids.cuda(), attention_mask=am.cuda(), input_features=fo["input_features"],
+                      input_features_mask=fo["input_features_mask"], max_new_tokens=4).cpu()
+    top2 = l32[:, -1].topk(2).values
+    if bool(((top2[:, 0] - top2[:, 1]) > 0.2).all()):
+        assert torch.equal(g[:, :ids.shape[1] + 1], g_ref[:, :ids.shape[1] + 1])
