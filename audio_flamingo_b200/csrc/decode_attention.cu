@@ -1,31 +1,41 @@
 // Single-query (decode step) GQA attention over the pre-allocated KV cache; replaces SDPA at q_len = 1
 // ([O] Q2M:227-238 -> SDPA:40-104) and the torch.cat cache growth (CACHE:119-120: the cache here is written in
-// place by rope_kv_append).  HBM-bound: every K and V byte of the live context is read exactly once per step.
+// place by the qkv-projection epilogue / rope_kv_append).  HBM-bound: every K and V byte of the live context is read
+// exactly once per step.
 //
-// One CTA = one (sequence, KV head, 128-key chunk) and serves all G = H/Hkv (<= 16) query heads sharing the KV head.
-// The problem is transposed so that the 128 keys / 128 output dims are the UMMA M dimension and the (padded) 16 query
-// heads are N:
+// One CTA = one (sequence, KV head, split) and serves all G = H/Hkv (<= 16) query heads sharing the KV head.  It streams
+// its share of the live 128-key chunks through a 3-stage TMA ring (K and V tiles of 32 KB each, up to 192 KB in flight
+// per SM) and keeps an online softmax, flash-decoding style.  The problem is transposed so that the 128 keys / 128
+// output dims are the UMMA M dimension and the (padded) 16 query heads are N:
 //     S^T[key, head] = K_tile[key, :] . Q[head, :]          tcgen05.mma 128x16x16 x 8,  A = K tile (K-major, via TMA)
 //     O^T[dim, head] = V_tile^T[dim, key] . P^T[key, head]   tcgen05.mma 128x16x16 x 8,  A = V tile read MN-major
-// so the K and V tiles stream HBM -> smem by TMA (2 x 32 KB in flight per CTA, 3 CTAs/SM) and never pass through
-// registers; the softmax over the chunk is a cross-lane reduction of 16 columns (thread = key = TMEM lane).
-// B*Hkv*ceil(Tmax/128) CTAs cover the GPU; the last-arriving chunk CTA of a (sequence, KV head) merges the chunk partials
-// (log-sum-exp combine) -- no separate combine kernel.
-// ctx_len lives in device memory so the launch parameters are step-invariant (CUDA-graph replay); chunks beyond the
-// live context exit immediately.  Cache rows beyond the live context must hold finite values (the cache is
-// zero-initialised): they are multiplied by P = 0.
+// so K and V never pass through registers.  Roles: warps 0-3 softmax + accumulation (thread = key lane for S, = output
+// dim lane for O), warp 4 issues the MMAs, warp 5 the TMA loads.  S, P and the per-chunk O are double-buffered so that
+// S_{i+1} = K_{i+1} Q^T and the loads run ahead of softmax_i, and O_i is folded into the register accumulator after
+// softmax_{i+1} has been handed to the tensor core (the chunk's P.V product is then long complete).
+// Splits: the host picks nz = min(chunks(Tmax), SMs / (B*Hkv)) so that B*Hkv*nz CTAs (one per SM, 207 KB of smem) cover
+// the GPU; the live chunk range [start/128, ceil(ctx/128)) of each sequence is divided evenly over the nz splits at run
+// time.  nz == 1 (config 2: 32 x 4 = 128 CTAs) writes the normalised output directly; otherwise every split writes an
+// (unnormalised o, max, sum) partial and the last-arriving split CTA of a (sequence, KV head) merges them (log-sum-exp
+// combine) -- no separate combine kernel.
+// ctx_len lives in device memory so the launch parameters are step-invariant (CUDA-graph replay).  Cache rows beyond
+// the live context must hold finite values (the cache is zero-initialised): they are multiplied by P = 0.
 // Algorithmic bytes per step: 2 (K,V) * Hkv * D * 2 B * ctx * B  (= 57344 B per token per sequence at 28 layers).
+#include <stdlib.h>
+
 #include "common.h"
 #include "ptx.cuh"
 
 namespace af3 {
 
-constexpr int DA_CHUNK = 128;    // keys per CTA
+constexpr int DA_CHUNK = 128;    // keys per ring stage
 constexpr int DA_NH = 16;        // query heads per KV head, padded (UMMA N)
-constexpr int DA_THREADS = 160;  // warps 0-3: softmax / epilogue (thread = TMEM lane), warp 4: TMA + MMA issue
+constexpr int DA_NS = 3;         // K/V ring stages
+constexpr int DA_THREADS = 192;  // warps 0-3: softmax / accumulate (thread = TMEM lane), warp 4: MMA issue, warp 5: TMA
 constexpr int DA_D = 128;
-constexpr int DA_SMEM = 2 * DA_CHUNK * DA_D * 2 /*K,V*/ + 2 * (DA_NH * 128) /*Q: 2 blocks of 16 x 128 B*/ +
-                        2 * (DA_NH * 128) /*P*/ + 1024 /*align*/ + 1024 /*barriers + reduction scratch*/;
+constexpr int DA_STAGE = 2 * DA_CHUNK * DA_D * 2;  // K tile + V tile
+constexpr int DA_SMEM = DA_NS * DA_STAGE + 2 * (DA_NH * 128) /*Q: 2 blocks of 16 x 128 B*/ +
+                        2 * 2 * (DA_NH * 128) /*P, double-buffered*/ + 1024 /*align*/ + 2048 /*barriers + reduction scratch*/;
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
@@ -36,16 +46,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         : "memory");
 }
 
-// Merge of the chunk partials of one (sequence, KV head), executed by the last-arriving chunk CTA.  Partial layout
-// [b][h][split][D + 4] = (unnormalised o[D] relative to the chunk max, chunk max (log2 domain), chunk sum, pad).
+// Merge of the split partials of one (sequence, KV head), executed by the last-arriving split CTA.  Partial layout
+// [b][h][split][D + 4] = (unnormalised o[D] relative to the split max, split max (log2 domain), split sum, pad).
 // Work item = (head, 4 output dims): G * 32 items over the CTA's threads; the loads of all splits of an item are
-// independent (two dependent rounds in total: maxima, then sums + outputs).  Chunks outside [start, ctx) never wrote
-// theirs and are skipped by index.  Resets the arrival counter.
+// independent (two dependent rounds in total: maxima, then sums + outputs).  Only splits [s_lo, s_hi) hold live keys;
+// the others never wrote theirs and are skipped by index.  Resets the arrival counter.
 __device__ __forceinline__ void combine_heads(const float* __restrict__ part, bf16* __restrict__ out, int* counters, int b, int hk,
-                                              int G, int H, int Hkv, int nsplit, int ctx, int start) {
+                                              int G, int H, int Hkv, int nsplit, int s_lo, int s_hi) {
     constexpr int D = DA_D, ST = D + 4, SB = 8;  // splits handled per unrolled block
     __threadfence();
-    const int s_lo = start / DA_CHUNK, s_hi = (ctx + DA_CHUNK - 1) / DA_CHUNK;  // chunks that hold live keys
     for (int item = threadIdx.x; item < G * (D / 4); item += blockDim.x) {
         const int g = item / (D / 4), dq = item % (D / 4);
         const int h = hk * G + g;
@@ -86,171 +95,257 @@ __device__ __forceinline__ void combine_heads(const float* __restrict__ part, bf
     if (threadIdx.x == 0) counters[b * Hkv + hk] = 0;
 }
 
-__global__ void __launch_bounds__(DA_THREADS)
+__global__ void __launch_bounds__(DA_THREADS, 1)
 decode_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                    const __grid_constant__ CUtensorMap map_v, float* __restrict__ part, bf16* __restrict__ out,
-                   int* __restrict__ counters, int H, int Hkv, int nsplit, const int* __restrict__ ctx_len_p,
+                   int* __restrict__ counters, int H, int Hkv, int nz, const int* __restrict__ ctx_len_p,
                    const int* __restrict__ kv_start, float scale_log2) {
     constexpr int D = DA_D;
     const int G = H / Hkv;
     const int b = blockIdx.x, hk = blockIdx.y, sp = blockIdx.z;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    pdl_launch_dependents();
-    pdl_wait();
-    const int ctx = *ctx_len_p;
-    const int start = kv_start ? kv_start[b] : 0;
-    const int j0 = sp * DA_CHUNK;
-    const int j_beg = max(j0, start), j_end = min(j0 + DA_CHUNK, ctx);
-    float* pbase = part + ((static_cast<size_t>(b) * H + hk * G) * nsplit + sp) * (D + 4);
-    if (j_beg >= j_end) {  // chunk entirely outside the live context: it only counts as arrived
-        __shared__ int last_flag;
-        if (tid == 0) last_flag = (atomicAdd(counters + b * Hkv + hk, 1) == nsplit - 1);
-        __syncthreads();
-        if (last_flag) combine_heads(part, out, counters, b, hk, G, H, Hkv, nsplit, ctx, start);
-        return;
-    }
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* sK = smem;                   // 2 blocks [128 keys x 128 B]
-    uint8_t* sV = sK + DA_CHUNK * D * 2;  // 2 blocks [128 keys x 128 B]
-    uint8_t* sQ = sV + DA_CHUNK * D * 2;  // 2 blocks [16 heads x 128 B]
-    uint8_t* sP = sQ + 2 * DA_NH * 128;   // 2 blocks [16 heads x 128 B]  (64 keys along each 128-byte row)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * DA_NH * 128);
-    uint64_t *qk_full = bars, *v_full = bars + 1, *s_full = bars + 2, *p_full = bars + 3, *o_full = bars + 4;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
-    float* red = reinterpret_cast<float*>(bars + 6);  // [2][4 warps][16 heads]
+    uint8_t* sKV = smem;                         // DA_NS stages of {K: 2 blocks [128 keys x 128 B], V: same}
+    uint8_t* sQ = sKV + DA_NS * DA_STAGE;        // 2 blocks [16 heads x 128 B]
+    uint8_t* sP = sQ + 2 * DA_NH * 128;          // 2 buffers x 2 blocks [16 heads x 128 B]  (64 keys along each 128-byte row)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * DA_NH * 128);
+    uint64_t *q_full = bars, *k_full = bars + 1, *v_full = k_full + DA_NS, *kv_empty = v_full + DA_NS,
+             *s_full = kv_empty + DA_NS, *p_full = s_full + 2, *o_full = p_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+    float* red = reinterpret_cast<float*>(bars) + 256;  // [2 parities][4 warps][16 heads] chunk maxima, then [4][16] sums
+    __shared__ int last_flag;
 
+    // ---- prologue (no global-memory reads: overlaps the tail of the previous kernel under PDL)
     if (tid == 128) {
         tma_prefetch_desc(&map_q);
         tma_prefetch_desc(&map_k);
         tma_prefetch_desc(&map_v);
-        mbar_init(qk_full, 1);
-        mbar_init(v_full, 1);
-        mbar_init(s_full, 1);
-        mbar_init(p_full, 128);
-        mbar_init(o_full, 1);
+        mbar_init(q_full, 1);
+        for (int s = 0; s < DA_NS; ++s) {
+            mbar_init(k_full + s, 1);
+            mbar_init(v_full + s, 1);
+            mbar_init(kv_empty + s, 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(s_full + s, 1);
+            mbar_init(p_full + s, 128);
+            mbar_init(o_full + s, 1);
+        }
         fence_barrier_init();
     }
     if (warp == 0) {
-        tmem_alloc(tmem_slot, 32);
+        tmem_alloc(tmem_slot, 64);
         tmem_relinquish();
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_S = *tmem_slot, tmem_O = tmem_S + DA_NH;
+    const uint32_t tmem_S = *tmem_slot, tmem_O = tmem_S + 2 * DA_NH;  // S0 S1 O0 O1, 16 columns each
+    pdl_launch_dependents();
+    pdl_wait();
 
-    if (warp == 4) {
-        if (lane == 0) {
-            // all three operands in flight at once
-            mbar_arrive_expect_tx(qk_full, DA_CHUNK * D * 2 + 2 * DA_NH * 128);
+    // ---- this CTA's share of the live chunks
+    const int ctx = *ctx_len_p;
+    const int start = kv_start ? kv_start[b] : 0;
+    const int c_lo = start / DA_CHUNK, c_hi = (ctx + DA_CHUNK - 1) / DA_CHUNK;
+    const int n_live = max(c_hi - c_lo, 0);
+    const int cps = (n_live + nz - 1) / nz;                    // chunks per split
+    const int n_used = cps > 0 ? (n_live + cps - 1) / cps : 0;  // splits that hold live keys
+    const int c_beg = c_lo + sp * cps;
+    const int n = max(min(c_hi, c_beg + cps) - c_beg, 0);
+
+    if (n > 0) {
+        if (warp == 5) {
+            if (lane == 0) {
+                mbar_arrive_expect_tx(q_full, 2 * DA_NH * 128);
 #pragma unroll
-            for (int db = 0; db < 2; ++db) {
-                tma_load_2d(sQ + db * DA_NH * 128, &map_q, qk_full, db * 64, b * (H + 2 * Hkv) + hk * G);
-                tma_load_3d(sK + db * 16384, &map_k, qk_full, db * 64, j0, b * Hkv + hk);
+                for (int db = 0; db < 2; ++db) tma_load_2d(sQ + db * DA_NH * 128, &map_q, q_full, db * 64, b * (H + 2 * Hkv) + hk * G);
+                for (int i = 0; i < n; ++i) {
+                    const int s = i % DA_NS;
+                    if (i >= DA_NS) mbar_wait(kv_empty + s, ((i / DA_NS) - 1) & 1);
+                    uint8_t* st = sKV + s * DA_STAGE;
+                    const int row = (c_beg + i) * DA_CHUNK;
+                    mbar_arrive_expect_tx(k_full + s, DA_CHUNK * D * 2);
+#pragma unroll
+                    for (int db = 0; db < 2; ++db) tma_load_3d(st + db * 16384, &map_k, k_full + s, db * 64, row, b * Hkv + hk);
+                    mbar_arrive_expect_tx(v_full + s, DA_CHUNK * D * 2);
+#pragma unroll
+                    for (int db = 0; db < 2; ++db) tma_load_3d(st + 32768 + db * 16384, &map_v, v_full + s, db * 64, row, b * Hkv + hk);
+                }
             }
-            mbar_arrive_expect_tx(v_full, DA_CHUNK * D * 2);
+            __syncwarp();
+        } else if (warp == 4) {
+            if (lane == 0) {
+                constexpr uint32_t idesc_s = make_idesc_bf16(128, DA_NH, 0, 0);
+                constexpr uint32_t idesc_o = make_idesc_bf16(128, DA_NH, 1, 0);  // A (= V tile) is MN-major
+                const uint32_t aKV = smem_u32(sKV), aQ = smem_u32(sQ), aP = smem_u32(sP);
+                // O^T_j = V_j^T . P_j^T  (fresh accumulator: the running output lives in registers)
+                auto issue_pv = [&](int j) {
+                    const int s = j % DA_NS;
+                    mbar_wait(p_full + (j & 1), (j >> 1) & 1);
+                    mbar_wait(v_full + s, (j / DA_NS) & 1);
+                    tc_fence_after();
+                    const uint32_t aV = aKV + s * DA_STAGE + 32768, aPj = aP + (j & 1) * (2 * DA_NH * 128);
 #pragma unroll
-            for (int db = 0; db < 2; ++db) tma_load_3d(sV + db * 16384, &map_v, v_full, db * 64, j0, b * Hkv + hk);
-            constexpr uint32_t idesc_s = make_idesc_bf16(128, DA_NH, 0, 0);
-            constexpr uint32_t idesc_o = make_idesc_bf16(128, DA_NH, 1, 0);  // A (= V tile) is MN-major
-            const uint32_t aK = smem_u32(sK), aQ = smem_u32(sQ), aV = smem_u32(sV), aP = smem_u32(sP);
-            // S^T = K . Q^T
-            mbar_wait(qk_full, 0);
-            tc_fence_after();
+                    for (int kk = 0; kk < DA_CHUNK / 16; ++kk)
+                        umma_bf16_ss(tmem_O + (j & 1) * DA_NH, make_smem_desc_sw128(aV + kk * 2048, 16384, 1024),
+                                     make_smem_desc_sw128(aPj + (kk >> 2) * (DA_NH * 128) + (kk & 3) * 32, 0, 1024), idesc_o, kk != 0);
+                    umma_commit(o_full + (j & 1));
+                    umma_commit(kv_empty + s);
+                };
+                mbar_wait(q_full, 0);
+                for (int i = 0; i < n; ++i) {
+                    const int s = i % DA_NS;
+                    // S^T_i = K_i . Q^T into S[i & 1]: that buffer was last read by softmax_{i-2}, whose P the previous
+                    // iteration's issue_pv(i - 2) has already waited for
+                    mbar_wait(k_full + s, (i / DA_NS) & 1);
+                    tc_fence_after();
+                    const uint32_t aK = aKV + s * DA_STAGE;
 #pragma unroll
-            for (int kk = 0; kk < D / 16; ++kk)
-                umma_bf16_ss(tmem_S, make_smem_desc_sw128(aK + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024),
-                             make_smem_desc_sw128(aQ + (kk >> 2) * (DA_NH * 128) + (kk & 3) * 32, 0, 1024), idesc_s, kk != 0);
-            umma_commit(s_full);
-            // O^T = V^T . P^T
-            mbar_wait(p_full, 0);
-            mbar_wait(v_full, 0);
-            tc_fence_after();
+                    for (int kk = 0; kk < D / 16; ++kk)
+                        umma_bf16_ss(tmem_S + (i & 1) * DA_NH, make_smem_desc_sw128(aK + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024),
+                                     make_smem_desc_sw128(aQ + (kk >> 2) * (DA_NH * 128) + (kk & 3) * 32, 0, 1024), idesc_s, kk != 0);
+                    umma_commit(s_full + (i & 1));
+                    if (i >= 1) issue_pv(i - 1);
+                }
+                issue_pv(n - 1);
+            }
+            __syncwarp();
+        } else {
+            // ---- online softmax: thread = key (TMEM lane) for S, = output dim for O; 16 columns = heads
+            const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+            float m_run[DA_NH], m_prev[DA_NH], l_thr[DA_NH], acc[DA_NH];
 #pragma unroll
-            for (int kk = 0; kk < DA_CHUNK / 16; ++kk)
-                umma_bf16_ss(tmem_O, make_smem_desc_sw128(aV + kk * 2048, 16384, 1024),
-                             make_smem_desc_sw128(aP + (kk >> 2) * (DA_NH * 128) + (kk & 3) * 32, 0, 1024), idesc_o, kk != 0);
-            umma_commit(o_full);
-        }
-        __syncwarp();
-    } else {
-        // ---- softmax over the chunk: thread = key (TMEM lane), 16 columns = heads
-        const int j = j0 + tid;
-        const bool valid = j >= j_beg && j < j_end;
-        const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
-        mbar_wait(s_full, 0);
-        tc_fence_after();
-        uint32_t sv[16];
-        tmem_ld16(tmem_S + lane_off, sv);
-        tmem_ld_wait();
-        float t[DA_NH], m[DA_NH], p[DA_NH];
+            for (int g = 0; g < DA_NH; ++g) {
+                m_run[g] = -INFINITY;
+                m_prev[g] = -INFINITY;
+                l_thr[g] = 0.f;
+                acc[g] = 0.f;
+            }
+            // acc is kept relative to the running max at the time of its last update (m_from); O_j is relative to m_to
+            auto accumulate = [&](int j, const float (&m_from)[DA_NH], const float (&m_to)[DA_NH]) {
+                mbar_wait(o_full + (j & 1), (j >> 1) & 1);
+                tc_fence_after();
+                uint32_t ov[16];
+                tmem_ld16(tmem_O + (j & 1) * DA_NH + lane_off, ov);
+                tmem_ld_wait();
 #pragma unroll
-        for (int g = 0; g < DA_NH; ++g) {
-            t[g] = (valid && g < G) ? __uint_as_float(sv[g]) * scale_log2 : -INFINITY;
-            float mx = t[g];
+                for (int g = 0; g < DA_NH; ++g) {
+                    if (g < G) {
+                        const float a = (m_from[g] == -INFINITY) ? 0.f : exp2f(m_from[g] - m_to[g]);
+                        acc[g] = acc[g] * a + __uint_as_float(ov[g]);
+                    }
+                }
+            };
+            float m_pp[DA_NH];  // running max two chunks back (= what acc is relative to when O_{i-1} is folded in)
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-            if (lane == 0) red[warp * DA_NH + g] = mx;
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int g = 0; g < DA_NH; ++g) m_pp[g] = -INFINITY;
+            for (int i = 0; i < n; ++i) {
+                const int j = (c_beg + i) * DA_CHUNK + tid;
+                const bool valid = j >= start && j < ctx;
+                float* redm = red + (i & 1) * 64;
+                mbar_wait(s_full + (i & 1), (i >> 1) & 1);
+                tc_fence_after();
+                uint32_t sv[16];
+                tmem_ld16(tmem_S + (i & 1) * DA_NH + lane_off, sv);
+                tmem_ld_wait();
+                float t[DA_NH];
 #pragma unroll
-        for (int g = 0; g < DA_NH; ++g) {
-            m[g] = fmaxf(fmaxf(red[g], red[DA_NH + g]), fmaxf(red[2 * DA_NH + g], red[3 * DA_NH + g]));
-            p[g] = (t[g] == -INFINITY) ? 0.f : exp2f(t[g] - m[g]);
-            float ps = p[g];
+                for (int g = 0; g < DA_NH; ++g) {
+                    if (g < G) {
+                        t[g] = valid ? __uint_as_float(sv[g]) * scale_log2 : -INFINITY;
+                        float mx = t[g];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
-            if (lane == 0) red[64 + warp * DA_NH + g] = ps;
-        }
-        // P^T[key = tid][head g] -> B tile [16 heads][128 keys], K-major, 128B swizzle: row g, key column tid
-        {
-            uint8_t* blk = sP + (tid >> 6) * (DA_NH * 128);
-            const int kc = tid & 63;
+                        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                        if (lane == 0) redm[warp * DA_NH + g] = mx;
+                    }
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                uint8_t* blk = sP + (i & 1) * (2 * DA_NH * 128) + (tid >> 6) * (DA_NH * 128);
+                const int kc = tid & 63;
 #pragma unroll
-            for (int g = 0; g < DA_NH; ++g)
-                *reinterpret_cast<bf16*>(blk + g * 128 + ((((kc >> 3) ^ (g & 7)) << 4) | ((kc & 7) << 1))) = __float2bfloat16_rn(p[g]);
-        }
-        fence_proxy_async_smem();
-        tc_fence_before();
-        mbar_arrive(p_full);
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // red[64..] complete
-        // ---- O^T[dim = tid][head] -> partial
-        mbar_wait(o_full, 0);
-        tc_fence_after();
-        uint32_t ov[16];
-        tmem_ld16(tmem_O + lane_off, ov);
-        tmem_ld_wait();
+                for (int g = 0; g < DA_NH; ++g) {
+                    float p = 0.f;
+                    if (g < G) {
+                        const float mc = fmaxf(fmaxf(redm[g], redm[DA_NH + g]), fmaxf(redm[2 * DA_NH + g], redm[3 * DA_NH + g]));
+                        const float m_new = fmaxf(m_run[g], mc);
+                        const float a = (m_run[g] == -INFINITY) ? 0.f : exp2f(m_run[g] - m_new);
+                        p = (t[g] == -INFINITY) ? 0.f : exp2f(t[g] - m_new);
+                        l_thr[g] = l_thr[g] * a + p;
+                        m_pp[g] = m_prev[g];
+                        m_prev[g] = m_run[g];
+                        m_run[g] = m_new;
+                    }
+                    // P^T[key = tid][head g] -> B tile [16 heads][128 keys], K-major, 128B swizzle: row g, key column tid
+                    *reinterpret_cast<bf16*>(blk + g * 128 + ((((kc >> 3) ^ (g & 7)) << 4) | ((kc & 7) << 1))) = __float2bfloat16_rn(p);
+                }
+                fence_proxy_async_smem();
+                tc_fence_before();
+                mbar_arrive(p_full + (i & 1));
+                // fold in the previous chunk's P.V (relative to m_prev = running max after chunk i-1)
+                if (i >= 1) accumulate(i - 1, m_pp, m_prev);
+            }
+            accumulate(n - 1, m_prev, m_run);
+            // ---- softmax denominators: sum the per-thread partial sums over the 128 key lanes
+            float* reds = red + 128;
 #pragma unroll
-        for (int g = 0; g < DA_NH; ++g) {
-            if (g < G) {
-                float* dst = pbase + static_cast<size_t>(g) * nsplit * (D + 4);
-                dst[tid] = __uint_as_float(ov[g]);
-                if (tid == 0) {
-                    dst[D] = m[g];
-                    dst[D + 1] = red[64 + g] + red[64 + DA_NH + g] + red[64 + 2 * DA_NH + g] + red[64 + 3 * DA_NH + g];
+            for (int g = 0; g < DA_NH; ++g) {
+                if (g < G) {
+                    float ls = l_thr[g];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) ls += __shfl_xor_sync(0xffffffffu, ls, o);
+                    if (lane == 0) reds[warp * DA_NH + g] = ls;
+                }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+            for (int g = 0; g < DA_NH; ++g) {
+                if (g < G) {
+                    const float L = reds[g] + reds[DA_NH + g] + reds[2 * DA_NH + g] + reds[3 * DA_NH + g];
+                    if (nz == 1) {
+                        out[(static_cast<size_t>(b) * H + hk * G + g) * D + tid] = __float2bfloat16_rn(L > 0.f ? acc[g] / L : 0.f);
+                    } else {
+                        float* dst = part + ((static_cast<size_t>(b) * H + hk * G + g) * nz + sp) * (D + 4);
+                        dst[tid] = acc[g];
+                        if (tid == 0) {
+                            dst[D] = m_run[g];
+                            dst[D + 1] = L;
+                        }
+                    }
                 }
             }
         }
     }
     tc_fence_before();
-    __threadfence();  // partials visible before this chunk is counted
+    if (nz > 1) __threadfence();  // partials visible before this split is counted
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_S, 32);
-    // ---- the last-arriving chunk CTA of this (sequence, KV head) merges all chunk partials (log-sum-exp combine):
+    if (warp == 0) tmem_dealloc(tmem_S, 64);
+    if (nz == 1) return;
+    // ---- the last-arriving split CTA of this (sequence, KV head) merges all split partials (log-sum-exp combine):
     //      replaces a separate combine kernel per layer
-    int* flag = reinterpret_cast<int*>(red);
-    if (tid == 0) *flag = (atomicAdd(counters + b * Hkv + hk, 1) == nsplit - 1);
+    if (tid == 0) last_flag = (atomicAdd(counters + b * Hkv + hk, 1) == nz - 1);
     __syncthreads();
-    if (*flag) combine_heads(part, out, counters, b, hk, G, H, Hkv, nsplit, ctx, start);
+    if (last_flag) combine_heads(part, out, counters, b, hk, G, H, Hkv, nz, 0, n_used);
 }
 
-static int n_splits(int Tmax) { return ceil_div(Tmax, DA_CHUNK); }
+static int n_chunks(int Tmax) { return ceil_div(Tmax, DA_CHUNK); }
 
-// scratch = chunk partials + one arrival counter per (sequence, KV head); the counters must be ZERO on first use (the kernel
-// leaves them zero)
+// splits per (sequence, KV head): enough CTAs to cover the SMs, never more than there are chunks.  AF3_DECODE_SPLITS
+// overrides (tests).
+static int pick_splits(int B, int Hkv, int Tmax) {
+    int nz = sm_count() / (B * Hkv);
+    if (const char* e = getenv("AF3_DECODE_SPLITS")) {
+        const int v = atoi(e);
+        if (v > 0) nz = v;
+    }
+    return nz < 1 ? 1 : (nz > n_chunks(Tmax) ? n_chunks(Tmax) : nz);
+}
+
+// scratch = split partials (sized for the maximum split count) + one arrival counter per (sequence, KV head); the
+// counters must be ZERO on first use (the kernel leaves them zero)
 static size_t partial_bytes(int B, int H, int D, int Tmax) {
-    return (static_cast<size_t>(B) * H * n_splits(Tmax) * (D + 4) * sizeof(float) + 255) & ~static_cast<size_t>(255);
+    return (static_cast<size_t>(B) * H * n_chunks(Tmax) * (D + 4) * sizeof(float) + 255) & ~static_cast<size_t>(255);
 }
 size_t decode_attention_scratch_bytes(int B, int H, int D, int Tmax) {
     return partial_bytes(B, H, D, Tmax) + static_cast<size_t>(B) * H * sizeof(int);
@@ -262,8 +357,8 @@ int decode_attention(cudaStream_t stream, const bf16* qkv, const bf16* k_cache, 
     AF3_REQUIRE(D == 128, "decode_attention: head_dim must be 128");
     AF3_REQUIRE(H % Hkv == 0 && H / Hkv <= DA_NH, "decode_attention: at most 16 query heads per KV head");
     AF3_REQUIRE(ctx_len != nullptr, "decode_attention: ctx_len must be a device pointer");
-    const int ns = n_splits(Tmax);
-    AF3_REQUIRE(ns <= 65535, "decode_attention: context too long");
+    AF3_REQUIRE(Hkv <= 65535, "decode_attention: too many KV heads");
+    const int nz = pick_splits(B, Hkv, Tmax);
     static bool configured = false;
     if (!configured) {
         AF3_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DA_SMEM));
@@ -278,10 +373,10 @@ int decode_attention(cudaStream_t stream, const bf16* qkv, const bf16* k_cache, 
     if (int e = make_tmap_3d(&mv, v_cache, D, Tmax, static_cast<uint64_t>(B) * Hkv, D, static_cast<uint64_t>(Tmax) * D, 64,
                              DA_CHUNK, 1))
         return e;
-    dim3 grid(B, Hkv, ns);
+    dim3 grid(B, Hkv, nz);
     int* counters = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(scratch) + partial_bytes(B, H, D, Tmax));
     AF3_CHECK_CUDA(launch_kernel(decode_attn_kernel, grid, dim3(DA_THREADS), DA_SMEM, stream, mq, mk, mv, scratch, out, counters, H,
-                                 Hkv, ns, ctx_len, kv_start, scale * 1.4426950408889634f));
+                                 Hkv, nz, ctx_len, kv_start, scale * 1.4426950408889634f));
     return 0;
 }
 

@@ -270,22 +270,40 @@ def test_rope_kv_append(ops):
     assert torch.equal(v_cache[:, :, :T].transpose(1, 2), v_ref)
 
 
-def test_decode_attention(ops):
-    B, H, Hkv, D, Tmax = 3, 28, 4, 128, 1024
-    ctx = 777
+@pytest.mark.parametrize(
+    "B,H,Hkv,Tmax,ctx,starts,splits",
+    [
+        (3, 28, 4, 1024, 777, [0, 100, 776], None),   # auto: one chunk per split
+        (3, 28, 4, 1024, 777, [0, 100, 776], 1),      # one CTA streams 7 chunks (ring wraps twice)
+        (3, 28, 4, 1024, 777, [0, 100, 776], 3),      # 3 / 3 / 1 chunks; row 2 has a single live key
+        (2, 16, 1, 2048, 1901, [5, 1300], 1),         # G = 16 (no padded heads), 15 chunks in one CTA
+        (2, 8, 4, 2048, 1537, [0, 640], 5),           # G = 2, uneven splits, last chunk holds one key
+        (40, 28, 4, 512, 300, None, None),            # B * Hkv > SM count -> nz = 1, more CTAs than SMs
+        (1, 28, 4, 128, 1, [0], None),                # a single key
+    ],
+)
+def test_decode_attention(ops, monkeypatch, B, H, Hkv, Tmax, ctx, starts, splits):
+    D = 128
+    if splits is None:
+        monkeypatch.delenv("AF3_DECODE_SPLITS", raising=False)
+    else:
+        monkeypatch.setenv("AF3_DECODE_SPLITS", str(splits))
     qkv = _rand((B, (H + 2 * Hkv) * D), 1.0, 43)
     k_cache, v_cache = _rand((B, Hkv, Tmax, D), 1.0, 44), _rand((B, Hkv, Tmax, D), 1.0, 45)
-    starts = torch.tensor([0, 100, 776], dtype=torch.int32, device="cuda")
+    starts_t = torch.tensor(starts if starts is not None else [0] * B, dtype=torch.int32, device="cuda")
     ctx_len = torch.tensor([ctx], dtype=torch.int32, device="cuda")
     out = torch.zeros((B, H * D), device="cuda", dtype=bf16)
     scratch = ops.decode_attention_scratch(B, H, D, Tmax, "cuda")
-    ops.decode_attention(qkv, k_cache, v_cache, out, scratch, B=B, H=H, Hkv=Hkv, D=D, ctx_len=ctx_len, kv_start=starts, scale=D ** -0.5)
+    for _ in range(2):  # second call: the arrival counters must have been left at zero
+        out.zero_()
+        ops.decode_attention(qkv, k_cache, v_cache, out, scratch, B=B, H=H, Hkv=Hkv, D=D, ctx_len=ctx_len,
+                             kv_start=starts_t if starts is not None else None, scale=D ** -0.5)
     q = qkv[:, :H * D].float().view(B, H, 1, D)
     k = k_cache[:, :, :ctx].float().repeat_interleave(H // Hkv, dim=1)
     v = v_cache[:, :, :ctx].float().repeat_interleave(H // Hkv, dim=1)
     mask = torch.ones((B, 1, 1, ctx), dtype=torch.bool, device="cuda")
     for b in range(B):
-        mask[b, :, :, :starts[b]] = False
+        mask[b, :, :, :starts_t[b]] = False
     ref = _sdpa_ref(q, k, v, D ** -0.5, mask).reshape(B, H * D)
     _close(out, ref, 2e-2, 1e-2, "decode attention")
 
