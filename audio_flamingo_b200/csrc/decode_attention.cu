@@ -95,6 +95,17 @@ __device__ __forceinline__ void combine_heads(const float* __restrict__ part, bf
     if (threadIdx.x == 0) counters[b * Hkv + hk] = 0;
 }
 
+// 2^x on the SFU (ex2.approx.ftz: relative error ~2^-22, far below the bf16 rounding of P); 2^-inf = +0
+__device__ __forceinline__ float da_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// NG = query heads handled per thread (8 when G <= 8, else 16).  The per-head loops are branch-free over NG so the NG
+// independent shuffle / SFU chains interleave: with one CTA per SM each softmax warp is alone on its scheduler and every
+// dependent-instruction latency is otherwise exposed (ncu r01b: 90 % of the softmax warps' samples sat in those chains).
+template <int NG>
 __global__ void __launch_bounds__(DA_THREADS, 1)
 decode_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                    const __grid_constant__ CUtensorMap map_v, float* __restrict__ part, bf16* __restrict__ out,
@@ -213,34 +224,40 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             }
             __syncwarp();
         } else {
-            // ---- online softmax: thread = key (TMEM lane) for S, = output dim for O; 16 columns = heads
+            // ---- online softmax: thread = key (TMEM lane) for S, = output dim for O; columns = heads
             const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
-            float m_run[DA_NH], m_prev[DA_NH], l_thr[DA_NH], acc[DA_NH];
+            float m_run[NG], m_prev[NG], m_pp[NG], l_thr[NG], acc[NG];
 #pragma unroll
-            for (int g = 0; g < DA_NH; ++g) {
-                m_run[g] = -INFINITY;
-                m_prev[g] = -INFINITY;
-                l_thr[g] = 0.f;
-                acc[g] = 0.f;
+            for (int g = 0; g < NG; ++g) {
+                m_run[g] = -INFINITY;   // running max after the current chunk
+                m_prev[g] = -INFINITY;  // ... one chunk back (what O_{i-1} is relative to)
+                m_pp[g] = -INFINITY;    // ... two chunks back (what acc is relative to when O_{i-1} is folded in)
+                l_thr[g] = 0.f;         // this key lane's share of the softmax denominator
+                acc[g] = 0.f;           // this output dim's running numerator
             }
-            // acc is kept relative to the running max at the time of its last update (m_from); O_j is relative to m_to
-            auto accumulate = [&](int j, const float (&m_from)[DA_NH], const float (&m_to)[DA_NH]) {
+            {   // P rows of heads >= NG are never written again: zero them once in both buffers
+                const int kc = tid & 63;
+#pragma unroll
+                for (int pb = 0; pb < 2; ++pb) {
+                    uint8_t* blk = sP + pb * (2 * DA_NH * 128) + (tid >> 6) * (DA_NH * 128);
+#pragma unroll
+                    for (int g = NG; g < DA_NH; ++g)
+                        *reinterpret_cast<bf16*>(blk + g * 128 + ((((kc >> 3) ^ (g & 7)) << 4) | ((kc & 7) << 1))) = __float2bfloat16_rn(0.f);
+                }
+            }
+            // acc is relative to m_from (the running max at its last update); O_j is relative to m_to
+            auto accumulate = [&](int j, const float (&m_from)[NG], const float (&m_to)[NG]) {
                 mbar_wait(o_full + (j & 1), (j >> 1) & 1);
                 tc_fence_after();
                 uint32_t ov[16];
                 tmem_ld16(tmem_O + (j & 1) * DA_NH + lane_off, ov);
                 tmem_ld_wait();
 #pragma unroll
-                for (int g = 0; g < DA_NH; ++g) {
-                    if (g < G) {
-                        const float a = (m_from[g] == -INFINITY) ? 0.f : exp2f(m_from[g] - m_to[g]);
-                        acc[g] = acc[g] * a + __uint_as_float(ov[g]);
-                    }
+                for (int g = 0; g < NG; ++g) {
+                    const float a = (m_from[g] == -INFINITY) ? 0.f : da_exp2(m_from[g] - m_to[g]);
+                    acc[g] = fmaf(acc[g], a, __uint_as_float(ov[g]));
                 }
             };
-            float m_pp[DA_NH];  // running max two chunks back (= what acc is relative to when O_{i-1} is folded in)
-#pragma unroll
-            for (int g = 0; g < DA_NH; ++g) m_pp[g] = -INFINITY;
             for (int i = 0; i < n; ++i) {
                 const int j = (c_beg + i) * DA_CHUNK + tid;
                 const bool valid = j >= start && j < ctx;
@@ -250,33 +267,36 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 uint32_t sv[16];
                 tmem_ld16(tmem_S + (i & 1) * DA_NH + lane_off, sv);
                 tmem_ld_wait();
-                float t[DA_NH];
+                float t[NG], mx[NG];
 #pragma unroll
-                for (int g = 0; g < DA_NH; ++g) {
-                    if (g < G) {
-                        t[g] = valid ? __uint_as_float(sv[g]) * scale_log2 : -INFINITY;
-                        float mx = t[g];
+                for (int g = 0; g < NG; ++g) {
+                    t[g] = (valid && g < G) ? __uint_as_float(sv[g]) * scale_log2 : -INFINITY;
+                    mx[g] = t[g];
+                }
 #pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-                        if (lane == 0) redm[warp * DA_NH + g] = mx;
-                    }
+                for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                    for (int g = 0; g < NG; ++g) mx[g] = fmaxf(mx[g], __shfl_xor_sync(0xffffffffu, mx[g], o));
+                }
+                if (lane < NG) {  // lane g publishes head g's warp maximum (all lanes hold it after the butterfly)
+                    float v = mx[0];
+#pragma unroll
+                    for (int g = 1; g < NG; ++g) v = (lane == g) ? mx[g] : v;
+                    redm[warp * DA_NH + lane] = v;
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 uint8_t* blk = sP + (i & 1) * (2 * DA_NH * 128) + (tid >> 6) * (DA_NH * 128);
                 const int kc = tid & 63;
 #pragma unroll
-                for (int g = 0; g < DA_NH; ++g) {
-                    float p = 0.f;
-                    if (g < G) {
-                        const float mc = fmaxf(fmaxf(redm[g], redm[DA_NH + g]), fmaxf(redm[2 * DA_NH + g], redm[3 * DA_NH + g]));
-                        const float m_new = fmaxf(m_run[g], mc);
-                        const float a = (m_run[g] == -INFINITY) ? 0.f : exp2f(m_run[g] - m_new);
-                        p = (t[g] == -INFINITY) ? 0.f : exp2f(t[g] - m_new);
-                        l_thr[g] = l_thr[g] * a + p;
-                        m_pp[g] = m_prev[g];
-                        m_prev[g] = m_run[g];
-                        m_run[g] = m_new;
-                    }
+                for (int g = 0; g < NG; ++g) {
+                    const float mc = fmaxf(fmaxf(redm[g], redm[DA_NH + g]), fmaxf(redm[2 * DA_NH + g], redm[3 * DA_NH + g]));
+                    const float m_new = fmaxf(m_run[g], mc);
+                    const float a = (m_run[g] == -INFINITY) ? 0.f : da_exp2(m_run[g] - m_new);
+                    const float p = (t[g] == -INFINITY) ? 0.f : da_exp2(t[g] - m_new);  // masked keys / padded heads -> 0
+                    l_thr[g] = fmaf(l_thr[g], a, p);
+                    m_pp[g] = m_prev[g];
+                    m_prev[g] = m_run[g];
+                    m_run[g] = m_new;
                     // P^T[key = tid][head g] -> B tile [16 heads][128 keys], K-major, 128B swizzle: row g, key column tid
                     *reinterpret_cast<bf16*>(blk + g * 128 + ((((kc >> 3) ^ (g & 7)) << 4) | ((kc & 7) << 1))) = __float2bfloat16_rn(p);
                 }
@@ -290,17 +310,19 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             // ---- softmax denominators: sum the per-thread partial sums over the 128 key lanes
             float* reds = red + 128;
 #pragma unroll
-            for (int g = 0; g < DA_NH; ++g) {
-                if (g < G) {
-                    float ls = l_thr[g];
+            for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) ls += __shfl_xor_sync(0xffffffffu, ls, o);
-                    if (lane == 0) reds[warp * DA_NH + g] = ls;
-                }
+                for (int g = 0; g < NG; ++g) l_thr[g] += __shfl_xor_sync(0xffffffffu, l_thr[g], o);
+            }
+            if (lane < NG) {
+                float v = l_thr[0];
+#pragma unroll
+                for (int g = 1; g < NG; ++g) v = (lane == g) ? l_thr[g] : v;
+                reds[warp * DA_NH + lane] = v;
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll
-            for (int g = 0; g < DA_NH; ++g) {
+            for (int g = 0; g < NG; ++g) {
                 if (g < G) {
                     const float L = reds[g] + reds[DA_NH + g] + reds[2 * DA_NH + g] + reds[3 * DA_NH + g];
                     if (nz == 1) {
@@ -361,7 +383,8 @@ int decode_attention(cudaStream_t stream, const bf16* qkv, const bf16* k_cache, 
     const int nz = pick_splits(B, Hkv, Tmax);
     static bool configured = false;
     if (!configured) {
-        AF3_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DA_SMEM));
+        AF3_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, DA_SMEM));
+        AF3_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, DA_SMEM));
         configured = true;
     }
     CUtensorMap mq, mk, mv;
@@ -375,8 +398,9 @@ int decode_attention(cudaStream_t stream, const bf16* qkv, const bf16* k_cache, 
         return e;
     dim3 grid(B, Hkv, nz);
     int* counters = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(scratch) + partial_bytes(B, H, D, Tmax));
-    AF3_CHECK_CUDA(launch_kernel(decode_attn_kernel, grid, dim3(DA_THREADS), DA_SMEM, stream, mq, mk, mv, scratch, out, counters, H,
-                                 Hkv, nz, ctx_len, kv_start, scale * 1.4426950408889634f));
+    auto kern = (H / Hkv <= 8) ? decode_attn_kernel<8> : decode_attn_kernel<16>;
+    AF3_CHECK_CUDA(launch_kernel(kern, grid, dim3(DA_THREADS), DA_SMEM, stream, mq, mk, mv, scratch, out, counters, H, Hkv, nz,
+                                 ctx_len, kv_start, scale * 1.4426950408889634f));
     return 0;
 }
 

@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import math
 import os
+import time
 from dataclasses import dataclass
 from typing import Optional
 
@@ -229,9 +230,21 @@ class AF3KVCache:
         self.v = torch.zeros_like(self.k)
         self.B, self.Tmax = B, Tmax
         self.length = 0
-        self.kv_start = None  # int32 [B]: left-padding length per sequence
+        # int32 [B]: left-padding length per sequence.  A persistent buffer (prefill copies into it) so that a captured decode
+        # graph, which holds its address, stays valid when the cache is reused for the next prompt.
+        self.kv_start = torch.zeros((B,), device=device, dtype=torch.int32)
         self.pos_dev = torch.zeros((1,), device=device, dtype=torch.int32)
         self.ctx_dev = torch.ones((1,), device=device, dtype=torch.int32)
+
+    def reset(self):
+        """Back to the state of a fresh cache (same buffers): rows are re-zeroed so that the kernels' invariant -- rows beyond the
+        live context are finite -- never depends on what an earlier prompt left behind (two async memsets, ~0.5 ms at config 2)."""
+        self.k.zero_()
+        self.v.zero_()
+        self.length = 0
+        self.kv_start.zero_()
+        self.pos_dev.zero_()
+        self.ctx_dev.fill_(1)
 
     def get_seq_length(self, layer_idx=0):
         return self.length
@@ -328,7 +341,10 @@ class Qwen2ForCausalLM(nn.Module):
         B, S, _ = inputs_embeds.shape
         if cache.length + S > cache.Tmax:
             raise AF3Error("KV cache too small for this prompt")
-        cache.kv_start = kv_start
+        if kv_start is None:
+            cache.kv_start.zero_()
+        else:
+            cache.kv_start.copy_(kv_start)
         h = self._layers(inputs_embeds.view(B * S, self.hid), B, S, cache, decode=False)
         cache.length += S
         cache.pos_dev.fill_(cache.length)
@@ -370,13 +386,20 @@ class AudioFlamingo3ForConditionalGeneration(nn.Module):
         if _cfg_get(config, "projector_hidden_act", "gelu") != "gelu":
             raise AF3Error("only projector_hidden_act='gelu' is implemented")
         self._graph = None
+        # KV cache + captured decode graph of the last generate() shape, kept between calls: capturing and instantiating the
+        # ~230-node step graph costs the launching thread 0.05-0.3 s during which the GPU idles (r01 bench host-gap logs), and a
+        # serving loop issues the same (batch, max length) shape over and over.  release_decode_state() frees it.
+        self._decode_state = None
         self.stage_events = None  # bench instrumentation: when a list, (name, cuda event) is appended at stage boundaries
+        self.stage_host_t = None  # ... and, when a list, (name, host perf_counter at enqueue time): GPU-bound vs launch-bound
 
     def _mark(self, name):
         if self.stage_events is not None:
             ev = torch.cuda.Event(enable_timing=True)
             ev.record()
             self.stage_events.append((name, ev))
+            if self.stage_host_t is not None:
+                self.stage_host_t.append((name, time.perf_counter()))
 
     # ---- construction from the reference model / a reference state_dict
     @classmethod
@@ -511,7 +534,17 @@ class AudioFlamingo3ForConditionalGeneration(nn.Module):
         x = self._prompt_embeds(input_ids, input_features, input_features_mask)
         self._mark("audio_done")
         kv_start = self._left_pad_starts(attention_mask, B, S, dev)
-        cache = lm.new_cache(B, S + max_new_tokens)
+        use_graph = bool(use_cuda_graph and max_new_tokens > 2)
+        key = (B, S + max_new_tokens, use_graph, os.environ.get("AF3_PDL", "1") != "0", str(dev))
+        st = self._decode_state
+        if st is not None and st["key"] == key:
+            cache, step_fn = st["cache"], st["step"]       # same buffers -> the captured graph is valid as it stands
+            cache.reset()
+        else:
+            self._decode_state = st = None                 # free the previous shape's cache and graph first
+            cache = lm.new_cache(B, S + max_new_tokens)
+            step_fn = self._decode_runner(B, cache, use_graph)
+            self._decode_state = {"key": key, "cache": cache, "step": step_fn}
         logits = lm.prefill(x, kv_start, cache, logits_to_keep=1).view(B, -1)           # GEN:3724 _prefill
         self._mark("prefill_done")
         out = torch.empty((B, S + max_new_tokens), device=dev, dtype=torch.int64)
@@ -524,7 +557,19 @@ class AudioFlamingo3ForConditionalGeneration(nn.Module):
             unfinished = torch.ones((B,), device=dev, dtype=torch.int64)
         kept_logits = [logits.clone()] if return_logits else None
         next_ids = ops.argmax(logits)                                                   # GEN:2793
-        step_fn = self._decode_runner(B, cache, use_cuda_graph and max_new_tokens > 2)
+        result = self._token_loop(step_fn, cache, out, next_ids, logits, kept_logits, eos, unfinished if eos is not None else None,
+                                  pad_token_id, S, max_new_tokens)
+        self._mark("decode_done")
+        if return_logits:
+            return result, torch.stack(kept_logits, 1)
+        return result
+
+    def release_decode_state(self):
+        """Frees the KV cache and decode graph kept from the last generate() call."""
+        self._decode_state = None
+
+    def _token_loop(self, step_fn, cache, out, next_ids, logits, kept_logits, eos, unfinished, pad_token_id, S, max_new_tokens):
+        return_logits = kept_logits is not None
         n_done = max_new_tokens
         for i in range(max_new_tokens):
             if eos is not None:
@@ -539,13 +584,11 @@ class AudioFlamingo3ForConditionalGeneration(nn.Module):
                 break
             logits, next_ids = step_fn(next_ids)   # one cached step incl. the greedy argmax (GEN:2793)
             cache.length += 1
+            if self.stage_host_t is not None:  # bench instrumentation: host time after enqueueing token i + 1
+                self.stage_host_t.append(("tok", time.perf_counter()))
             if return_logits:
                 kept_logits.append(logits.clone())
-        result = out[:, : S + n_done]
-        self._mark("decode_done")
-        if return_logits:
-            return result, torch.stack(kept_logits, 1)
-        return result
+        return out[:, : S + n_done]
 
     def _decode_runner(self, B, cache, use_graph):
         """Returns step(next_ids[int64 B]) -> (fp32 logits [B, V], greedy ids [B]).  With use_graph the whole step (embedding

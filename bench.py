@@ -48,6 +48,18 @@ def dist_env():
     return rank, world, local
 
 
+def cpu_throttle_snapshot():
+    """cgroup CPU-quota throttling counters of this container (v2 or v1 path); None when not exposed."""
+    for path in ("/sys/fs/cgroup/cpu.stat", "/sys/fs/cgroup/cpu/cpu.stat", "/sys/fs/cgroup/cpu,cpuacct/cpu.stat"):
+        try:
+            kv = dict(ln.split() for ln in open(path).read().strip().splitlines())
+            return {"nr_throttled": int(kv.get("nr_throttled", 0)),
+                    "throttled_ms": int(kv.get("throttled_usec", int(kv.get("throttled_time", 0)) // 1000)) / 1e3}
+        except Exception:
+            continue
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (profiling recipe)."""
 
@@ -186,6 +198,8 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_t = []  # per timed step: [(stage name, host perf_counter when that stage boundary was ENQUEUED)]
+
     def timed(n_steps, from_host, collect_stages=False):
         barrier()
         ops.LAUNCHES = 0
@@ -198,10 +212,13 @@ def run_ours(args):
                 ev = torch.cuda.Event(enable_timing=True)
                 ev.record()
                 model.stage_events.append(("step_start", ev))
+                model.stage_host_t = []
             step(from_host)
             if collect_stages:
                 stages.append(model.stage_events)
+                host_t.append(model.stage_host_t)
                 model.stage_events = None
+                model.stage_host_t = None
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -213,13 +230,26 @@ def run_ours(args):
             ms = float(t.item())
         return ms, ops.LAUNCHES, stages
 
+    # The clock sampler (one long-lived `nvidia-smi -lms` process) is started BEFORE the warm-up steps: its start-up (NVML attach)
+    # stalls work submission on the GPU for a while, which must not land inside the timed region.  AF3_BENCH_SAMPLER=late
+    # restores the old placement (right before the timed steps), =off disables it (diagnostics only: clocks is then null).
+    sampler_mode = os.environ.get("AF3_BENCH_SAMPLER", "early")
+    sampler = ClockSampler(local)
+    if rank == 0 and sampler_mode == "early":
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         step(False)
-    sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and sampler_mode == "early":
+        sampler.lines.clear()  # keep only the samples taken during the timed region
+    if rank == 0 and sampler_mode == "late":
         sampler.start()
+    thr0 = cpu_throttle_snapshot()
     ms_dev, launches, stages = timed(args.steps, from_host=False, collect_stages=True)
-    clocks = sampler.stop() if rank == 0 else None
+    thr1 = cpu_throttle_snapshot()
+    host_cpu = {"cpus_allowed": len(os.sched_getaffinity(0)), "loadavg": os.getloadavg()[0],
+                "throttled_during_timed": None if (thr0 is None or thr1 is None) else
+                {"nr": thr1["nr_throttled"] - thr0["nr_throttled"], "ms": round(thr1["throttled_ms"] - thr0["throttled_ms"], 1)}}
+    clocks = sampler.stop() if (rank == 0 and sampler_mode != "off") else None
     step(True)  # warm the host path (pinned staging, H2D)
     ms_e2e, _, _ = timed(args.steps, from_host=True)
 
@@ -245,7 +275,7 @@ def run_ours(args):
     # stage breakdown (rank 0, mean over steps)
     names = ["mel", "encode_project", "prefill", "decode"]
     keys = [("step_start", "mel_done"), ("start", "audio_done"), ("audio_done", "prefill_done"), ("prefill_done", "decode_done")]
-    stage_ms = {}
+    stage_ms, stage_ms_per_step = {}, {}
     for nm, (a, b) in zip(names, keys):
         vals = []
         for evs in stages:
@@ -253,6 +283,22 @@ def run_ours(args):
             if a in d and b in d:
                 vals.append(d[a].elapsed_time(d[b]))
         stage_ms[nm] = sum(vals) / len(vals) if vals else None
+        stage_ms_per_step[nm] = [round(v, 3) for v in vals]  # one entry per timed step: shows whether a slow mean is one step or all
+    # host-side time spent ENQUEUEING the decode stage of each step (no sync inside): ~= the GPU time when launch-bound,
+    # much smaller when the GPU is the bottleneck
+    host_decode_enqueue_ms, host_token_gaps = [], []
+    for ht in host_t:
+        d = {k: v for k, v in (ht or []) if k != "tok"}
+        if "prefill_done" in d and "decode_done" in d:
+            host_decode_enqueue_ms.append(round((d["decode_done"] - d["prefill_done"]) * 1e3, 3))
+            # host time between consecutive token enqueues (token 1 = eager warm step, token 2 = graph capture, then replays)
+            ts = [d["prefill_done"]] + [v for k, v in ht if k == "tok"]
+            gaps = [(b - a) * 1e3 for a, b in zip(ts, ts[1:])]
+            if gaps:
+                imax = max(range(len(gaps)), key=gaps.__getitem__)
+                host_token_gaps.append({"first3_ms": [round(g, 1) for g in gaps[:3]], "median_ms": round(statistics.median(gaps), 3),
+                                        "max_ms": round(gaps[imax], 1), "max_at_token": imax + 1,
+                                        "n_over_20ms": sum(g > 20 for g in gaps[3:])})
     audio_ms = (stage_ms["mel"] or 0) + (stage_ms["encode_project"] or 0)
     audio_s_per_s = B * world * CLIP_S / (audio_ms / 1e3) if audio_ms else None
     decode_tok_s = B * world * (NEW_TOKENS - 1) / (stage_ms["decode"] / 1e3) if stage_ms["decode"] else None
@@ -341,7 +387,7 @@ def run_ours(args):
         "e2e": {"value": n_tok_total / (ms_e2e / args.steps / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": int(wave_host.numel() * 4 + ids_host.numel() * 8),
                 "d2h_bytes_per_step": int(tokens_host.numel() * 8), "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
-        "audio_s_per_s": audio_s_per_s, "decode_tok_s": decode_tok_s, "stage_ms": stage_ms,
+        "audio_s_per_s": audio_s_per_s, "decode_tok_s": decode_tok_s, "stage_ms": stage_ms, "stage_ms_per_step": stage_ms_per_step, "host_decode_enqueue_ms": host_decode_enqueue_ms, "host_token_gaps": host_token_gaps, "host_cpu": host_cpu,
         "roofline": roofline, "roofline_decode_step": decode_roofline, "kernels": table[:14], "decode_step_kernel_ms": dec,
         "cpu_baseline": cpu, "clocks": clocks,
     }

@@ -20,6 +20,13 @@ starts = torch.zeros((B,), dtype=torch.int32, device="cuda")
 out = torch.zeros((B, H * D), device="cuda", dtype=bf16)
 scratch = ops.decode_attention_scratch(B, H, D, Tmax, "cuda")
 res = {}
+if os.environ.get("AF3_MB_EAGER"):  # for ncu: plain launches at ctx 780, auto splits, no graph
+    ctx_len = torch.tensor([780], dtype=torch.int32, device="cuda")
+    for _ in range(3):
+        for k, v in caches:
+            ops.decode_attention(qkv, k, v, out, scratch, B=B, H=H, Hkv=Hkv, D=D, ctx_len=ctx_len, kv_start=starts, scale=D ** -0.5)
+    torch.cuda.synchronize()
+    sys.exit(0)
 for ctx in (780, 908):
     ctx_len = torch.tensor([ctx], dtype=torch.int32, device="cuda")
     for splits in (None, 1, 2, 8):

@@ -251,3 +251,34 @@ def test_long_audio_five_windows(O):
     top2 = l32[:, -1].topk(2).values
     if bool(((top2[:, 0] - top2[:, 1]) > 0.2).all()):
         assert torch.equal(g[:, :ids.shape[1] + 1], g_ref[:, :ids.shape[1] + 1])
+
+
+def test_generate_reuses_decode_graph_across_calls(O):
+    """generate() keeps the KV cache + captured decode graph of the last (batch, max length) shape.  A second prompt of the same
+    shape must replay that graph (no re-capture) and give exactly what a fresh model instance gives; the first prompt run again
+    must reproduce itself bit for bit (nothing of prompt B survives in the reused cache); another shape rebuilds the state."""
+    from audio_flamingo_b200 import AudioFlamingo3ForConditionalGeneration
+
+    ref32 = O.hf_model("mid", seed=6, sharpen=8.0)
+    cfg = ref32.config
+    _, fa, ma, ids_a, am_a = _inputs(O, cfg, [30.0, 9.0], seed=11)
+    _, fb, mb, ids_b, am_b = _inputs(O, cfg, [30.0, 9.0], seed=12)   # same clip lengths -> same prompt shape, other content
+    assert ids_a.shape == ids_b.shape and not torch.equal(ids_a, ids_b)
+    kw = lambda f, m, i, a, n=10: dict(input_ids=i.cuda(), attention_mask=a.cuda(), input_features=f.cuda(),  # noqa: E731
+                                        input_features_mask=m.cuda(), max_new_tokens=n, return_logits=True)
+    ours = AudioFlamingo3ForConditionalGeneration.from_reference(ref32, device="cuda")
+    fresh = AudioFlamingo3ForConditionalGeneration.from_reference(ref32, device="cuda")
+    ga1, la1 = ours.generate(**kw(fa, ma, ids_a, am_a))
+    st = ours._decode_state
+    assert st is not None and st["key"][:2] == (2, ids_a.shape[1] + 10)
+    gb, lb = ours.generate(**kw(fb, mb, ids_b, am_b))
+    assert ours._decode_state is st, "same shape: cache and graph must be reused, not rebuilt"
+    gb_fresh, lb_fresh = fresh.generate(**kw(fb, mb, ids_b, am_b))
+    assert torch.equal(gb, gb_fresh) and torch.equal(lb, lb_fresh)
+    ga2, la2 = ours.generate(**kw(fa, ma, ids_a, am_a))
+    assert torch.equal(ga1, ga2) and torch.equal(la1, la2)
+    gc_, _ = ours.generate(**kw(fa, ma, ids_a, am_a, n=6))
+    assert ours._decode_state is not st and ours._decode_state["key"][1] == ids_a.shape[1] + 6
+    assert torch.equal(gc_, ga1[:, : ids_a.shape[1] + 6])
+    ours.release_decode_state()
+    assert ours._decode_state is None
