@@ -423,6 +423,7 @@ class AudioFlamingo3ForConditionalGeneration(nn.Module):
         self.audio_tower._packed = None
         self.language_model._packed = None
         self._graph = None
+        self._decode_state = None  # its graph holds the addresses of the packed weights just dropped
         return self
 
     def get_input_embeddings(self):
@@ -535,7 +536,10 @@ class AudioFlamingo3ForConditionalGeneration(nn.Module):
         self._mark("audio_done")
         kv_start = self._left_pad_starts(attention_mask, B, S, dev)
         use_graph = bool(use_cuda_graph and max_new_tokens > 2)
-        key = (B, S + max_new_tokens, use_graph, os.environ.get("AF3_PDL", "1") != "0", str(dev))
+        # the captured graph holds raw addresses: key it on the weight storages too, so a re-pack (load_reference_state_dict) or
+        # a move (.to()) can never leave a stale graph replaying against freed memory
+        key = (B, S + max_new_tokens, use_graph, os.environ.get("AF3_PDL", "1") != "0", str(dev),
+               lm.lm_head.weight.data_ptr(), lm._packed[0][0].data_ptr(), lm._packed[-1][2].data_ptr())
         st = self._decode_state
         if st is not None and st["key"] == key:
             cache, step_fn = st["cache"], st["step"]       # same buffers -> the captured graph is valid as it stands

@@ -280,5 +280,14 @@ def test_generate_reuses_decode_graph_across_calls(O):
     gc_, _ = ours.generate(**kw(fa, ma, ids_a, am_a, n=6))
     assert ours._decode_state is not st and ours._decode_state["key"][1] == ids_a.shape[1] + 6
     assert torch.equal(gc_, ga1[:, : ids_a.shape[1] + 6])
+    # new weights into the same instance: the kept graph points at the old packed weights and must not be replayed
+    ref_w = O.hf_model("mid", seed=7, sharpen=8.0)
+    gw_fresh, lw_fresh = AudioFlamingo3ForConditionalGeneration.from_reference(ref_w, device="cuda").generate(**kw(fa, ma, ids_a, am_a))
+    ours.generate(**kw(fa, ma, ids_a, am_a))                      # leaves a live state for this shape
+    ours.load_reference_state_dict({k: v for k, v in ref_w.state_dict().items()})
+    assert ours._decode_state is None
+    gw, lw = ours.generate(**kw(fa, ma, ids_a, am_a))
+    assert torch.equal(gw, gw_fresh) and torch.equal(lw, lw_fresh)
+    assert not torch.equal(lw, la1)
     ours.release_decode_state()
     assert ours._decode_state is None
