@@ -156,6 +156,8 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
 
+        # NCCL writes its version banner / debug lines to stdout by default; stdout carries the ONE JSON line of the contract
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     from audio_flamingo_b200 import AF3FeatureExtractor, AudioFlamingo3ForConditionalGeneration, ops
     from audio_flamingo_b200.sharding import gather_tokens
