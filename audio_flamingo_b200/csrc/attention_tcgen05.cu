@@ -42,7 +42,11 @@ struct AttnCfg {
     static constexpr int Q_BYTES = AT_BM * D * 2;
     static constexpr int P_BYTES = AT_BM * AT_BN * 2;
     static constexpr int SMEM_BYTES = Q_BYTES + P_BYTES + AT_NSTG * TILE_BYTES + 1024 + 128 + 768 * 4;
-    static constexpr int TMEM_COLS = 256;                  // S: 128 cols, O: D cols
+    // D = 128 fits one CTA per SM (165 KB of smem), so nothing else fills the tensor pipe while its softmax runs: S is
+    // double-buffered in TMEM there and Q.K_{t+1}^T is issued while softmax_t is in progress.  D = 64 runs two CTAs per SM
+    // (2 x 256 columns), which overlap each other instead.
+    static constexpr bool DOUBLE_S = (D == 128);
+    static constexpr int TMEM_COLS = DOUBLE_S ? 512 : 256; // S: 128 cols (x2 when double-buffered), O: D cols
 };
 
 __device__ __forceinline__ void attn_tile_range(const AttnArgs& a, int b, int q0, int& j_lo, int& j_hi) {
@@ -70,8 +74,8 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     uint64_t* q_full = bars;
     uint64_t* kv_full = bars + 1;
     uint64_t* kv_empty = kv_full + AT_NSTG;
-    uint64_t* s_full = kv_empty + AT_NSTG;
-    uint64_t* p_full = s_full + 1;
+    uint64_t* s_full = kv_empty + AT_NSTG;   // [2] (the second one only used with DOUBLE_S)
+    uint64_t* p_full = s_full + 2;
     uint64_t* o_full = p_full + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
     float* sMax = reinterpret_cast<float*>(bars + 16);  // [2 tiles][2 halves][128 rows] maxima + [2][128] row sums
@@ -90,6 +94,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             mbar_init(&kv_empty[i], 1);
         }
         mbar_init(s_full, 1);
+        mbar_init(s_full + 1, 1);
         mbar_init(p_full, 256);
         mbar_init(o_full, 1);
         fence_barrier_init();
@@ -102,7 +107,8 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + AT_BN;
+    constexpr bool DS = Cfg::DOUBLE_S;
+    const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + (DS ? 2 * AT_BN : AT_BN);
 
     int j_lo, j_hi;
     attn_tile_range(a, b, q0, j_lo, j_hi);
@@ -143,45 +149,48 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             constexpr uint32_t idesc_o = make_idesc_bf16(AT_BM, D, 0, 1);  // B (= V) is MN-major
             const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
             mbar_wait(q_full, 0);
-            int slot = 0;
-            uint32_t phase = 0;
-            for (int t = 0; t < n_tiles; ++t) {
-                // ---- S = Q K^T
-                mbar_wait(&kv_full[slot], phase);
+            // ring bookkeeping: K_t is load 2t, V_t is load 2t+1 of the producer's sequence; load i lives in slot i % AT_NSTG
+            // with phase (i / AT_NSTG) & 1 (consumption order differs from load order when S is double-buffered)
+            auto issue_qk = [&](int t) {   // S[t & 1 if DS else 0] = Q K_t^T
+                const int i = 2 * t, slot = i % AT_NSTG;
+                mbar_wait(&kv_full[slot], (i / AT_NSTG) & 1);
                 tc_fence_after();
-                {
-                    const uint32_t aK = smem_u32(sKV + slot * Cfg::TILE_BYTES);
+                const uint32_t aK = smem_u32(sKV + slot * Cfg::TILE_BYTES);
+                const uint32_t dS = tmem_S + (DS ? (t & 1) * AT_BN : 0);
 #pragma unroll
-                    for (int kk = 0; kk < D / 16; ++kk) {
-                        const uint32_t off = (kk >> 2) * 16384 + (kk & 3) * 32;
-                        umma_bf16_ss(tmem_S, make_smem_desc_sw128(aQ + off, 0, 1024), make_smem_desc_sw128(aK + off, 0, 1024),
-                                     idesc_s, kk != 0);
-                    }
-                    umma_commit(&kv_empty[slot]);
-                    umma_commit(s_full);
+                for (int kk = 0; kk < D / 16; ++kk) {
+                    const uint32_t off = (kk >> 2) * 16384 + (kk & 3) * 32;
+                    umma_bf16_ss(dS, make_smem_desc_sw128(aQ + off, 0, 1024), make_smem_desc_sw128(aK + off, 0, 1024), idesc_s, kk != 0);
                 }
-                if (++slot == AT_NSTG) {
-                    slot = 0;
-                    phase ^= 1;
-                }
-                // ---- O += P V
+                umma_commit(&kv_empty[slot]);
+                umma_commit(s_full + (DS ? (t & 1) : 0));
+            };
+            auto issue_pv = [&](int t) {   // O += P_t V_t
+                const int i = 2 * t + 1, slot = i % AT_NSTG;
                 mbar_wait(p_full, t & 1);
-                mbar_wait(&kv_full[slot], phase);
+                mbar_wait(&kv_full[slot], (i / AT_NSTG) & 1);
                 tc_fence_after();
-                {
-                    const uint32_t aV = smem_u32(sKV + slot * Cfg::TILE_BYTES);
+                const uint32_t aV = smem_u32(sKV + slot * Cfg::TILE_BYTES);
 #pragma unroll
-                    for (int kk = 0; kk < AT_BN / 16; ++kk) {
-                        const uint64_t adesc = make_smem_desc_sw128(aP + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024);
-                        const uint64_t bdesc = make_smem_desc_sw128(aV + kk * 2048, 16384, 1024);
-                        umma_bf16_ss(tmem_O, adesc, bdesc, idesc_o, (t | kk) != 0);
-                    }
-                    umma_commit(&kv_empty[slot]);
-                    umma_commit(o_full);
+                for (int kk = 0; kk < AT_BN / 16; ++kk) {
+                    const uint64_t adesc = make_smem_desc_sw128(aP + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024);
+                    const uint64_t bdesc = make_smem_desc_sw128(aV + kk * 2048, 16384, 1024);
+                    umma_bf16_ss(tmem_O, adesc, bdesc, idesc_o, (t | kk) != 0);
                 }
-                if (++slot == AT_NSTG) {
-                    slot = 0;
-                    phase ^= 1;
+                umma_commit(&kv_empty[slot]);
+                umma_commit(o_full);
+            };
+            if (DS) {
+                // S buffer (t+1)&1 was last read by softmax_{t-1}, whose P the previous iteration's issue_pv(t-1) waited for
+                issue_qk(0);
+                for (int t = 0; t < n_tiles; ++t) {
+                    if (t + 1 < n_tiles) issue_qk(t + 1);
+                    issue_pv(t);
+                }
+            } else {
+                for (int t = 0; t < n_tiles; ++t) {
+                    issue_qk(t);
+                    issue_pv(t);
                 }
             }
         }
@@ -200,13 +209,14 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         const int causal_hi = a.causal ? qi + (a.Tk - a.Tq) : 0x7fffffff;  // last visible key (inclusive)
         float m_ref = -INFINITY, l_run = 0.f;   // l_run: partial row sum over this thread's columns
         const float sl2 = a.scale_log2;
-        const uint32_t s_col = tmem_S + lane_off + half * 64;
+        const uint32_t s_col0 = tmem_S + lane_off + half * 64;
         constexpr int OC = D / 2;               // O columns owned by this thread (rescale / epilogue)
         const uint32_t o_col = tmem_O + lane_off + half * OC;
 
         for (int t = 0; t < n_tiles; ++t) {
             const int k0 = (j_lo + t) * AT_BN;
-            mbar_wait(s_full, t & 1);
+            const uint32_t s_col = s_col0 + (DS ? (t & 1) * AT_BN : 0);
+            mbar_wait(s_full + (DS ? (t & 1) : 0), DS ? ((t >> 1) & 1) : (t & 1));
             tc_fence_after();
             const bool need_mask = (k0 < kvs) || (k0 + AT_BN > kvl) || (a.causal && k0 + AT_BN - 1 > q0 + (a.Tk - a.Tq));
             // keys visible to this row inside the tile: local index in [vlo, vhi]  (one unsigned compare per element)

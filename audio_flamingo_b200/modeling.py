@@ -386,7 +386,7 @@ class AudioFlamingo3ForConditionalGeneration(nn.Module):
         if _cfg_get(config, "projector_hidden_act", "gelu") != "gelu":
             raise AF3Error("only projector_hidden_act='gelu' is implemented")
         self._graph = None
-        # KV cache + captured decode graph of the last generate() shape, kept between calls: capturing and instantiating the
+        # KV cache + captured decode graph of the last generate() (batch, capacity bucket), kept between calls: capturing and instantiating the
         # ~230-node step graph costs the launching thread 0.05-0.3 s during which the GPU idles (r01 bench host-gap logs), and a
         # serving loop issues the same (batch, max length) shape over and over.  release_decode_state() frees it.
         self._decode_state = None
@@ -536,9 +536,13 @@ class AudioFlamingo3ForConditionalGeneration(nn.Module):
         self._mark("audio_done")
         kv_start = self._left_pad_starts(attention_mask, B, S, dev)
         use_graph = bool(use_cuda_graph and max_new_tokens > 2)
+        # Cache capacity is rounded up to a multiple of 256 rows: the captured graph depends on the capacity (cache pitch in the
+        # tensor maps, scratch sizes) but not on the prompt length, so prompts of different lengths that fall into the same
+        # bucket reuse one cache + graph.  The kernels only ever touch the live rows, the extra capacity costs memory only.
+        Tmax = -(-(S + max_new_tokens) // 256) * 256
         # the captured graph holds raw addresses: key it on the weight storages too, so a re-pack (load_reference_state_dict) or
         # a move (.to()) can never leave a stale graph replaying against freed memory
-        key = (B, S + max_new_tokens, use_graph, os.environ.get("AF3_PDL", "1") != "0", str(dev),
+        key = (B, Tmax, use_graph, os.environ.get("AF3_PDL", "1") != "0", str(dev),
                lm.lm_head.weight.data_ptr(), lm._packed[0][0].data_ptr(), lm._packed[-1][2].data_ptr())
         st = self._decode_state
         if st is not None and st["key"] == key:
@@ -546,7 +550,7 @@ class AudioFlamingo3ForConditionalGeneration(nn.Module):
             cache.reset()
         else:
             self._decode_state = st = None                 # free the previous shape's cache and graph first
-            cache = lm.new_cache(B, S + max_new_tokens)
+            cache = lm.new_cache(B, Tmax)
             step_fn = self._decode_runner(B, cache, use_graph)
             self._decode_state = {"key": key, "cache": cache, "step": step_fn}
         logits = lm.prefill(x, kv_start, cache, logits_to_keep=1).view(B, -1)           # GEN:3724 _prefill

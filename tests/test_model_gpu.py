@@ -270,16 +270,28 @@ def test_generate_reuses_decode_graph_across_calls(O):
     fresh = AudioFlamingo3ForConditionalGeneration.from_reference(ref32, device="cuda")
     ga1, la1 = ours.generate(**kw(fa, ma, ids_a, am_a))
     st = ours._decode_state
-    assert st is not None and st["key"][:2] == (2, ids_a.shape[1] + 10)
+    cap = lambda n: -(-n // 256) * 256  # noqa: E731  (cache capacity bucket)
+    assert st is not None and st["key"][:2] == (2, cap(ids_a.shape[1] + 10))
     gb, lb = ours.generate(**kw(fb, mb, ids_b, am_b))
     assert ours._decode_state is st, "same shape: cache and graph must be reused, not rebuilt"
     gb_fresh, lb_fresh = fresh.generate(**kw(fb, mb, ids_b, am_b))
     assert torch.equal(gb, gb_fresh) and torch.equal(lb, lb_fresh)
     ga2, la2 = ours.generate(**kw(fa, ma, ids_a, am_a))
     assert torch.equal(ga1, ga2) and torch.equal(la1, la2)
+    # another prompt length / token budget inside the same capacity bucket: still the same graph
     gc_, _ = ours.generate(**kw(fa, ma, ids_a, am_a, n=6))
-    assert ours._decode_state is not st and ours._decode_state["key"][1] == ids_a.shape[1] + 6
+    assert cap(ids_a.shape[1] + 6) == cap(ids_a.shape[1] + 10) and ours._decode_state is st
     assert torch.equal(gc_, ga1[:, : ids_a.shape[1] + 6])
+    _, fs, ms, ids_s, am_s = _inputs(O, cfg, [30.0, 9.5], seed=11)      # 9.5 s instead of 9 s: a longer left-padded row
+    if cap(ids_s.shape[1] + 10) == cap(ids_a.shape[1] + 10) and ids_s.shape != ids_a.shape:
+        gs, ls = ours.generate(**kw(fs, ms, ids_s, am_s))
+        assert ours._decode_state is st
+        gs_fresh, ls_fresh = fresh.generate(**kw(fs, ms, ids_s, am_s))
+        assert torch.equal(gs, gs_fresh) and torch.equal(ls, ls_fresh)
+    # a different capacity bucket rebuilds the state
+    gd, _ = ours.generate(**kw(fa, ma, ids_a, am_a, n=10 + 256))
+    assert ours._decode_state is not st and ours._decode_state["key"][1] == cap(ids_a.shape[1] + 266)
+    assert torch.equal(gd[:, : ids_a.shape[1] + 10], ga1)
     # new weights into the same instance: the kept graph points at the old packed weights and must not be replayed
     ref_w = O.hf_model("mid", seed=7, sharpen=8.0)
     gw_fresh, lw_fresh = AudioFlamingo3ForConditionalGeneration.from_reference(ref_w, device="cuda").generate(**kw(fa, ma, ids_a, am_a))
