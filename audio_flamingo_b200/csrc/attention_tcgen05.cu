@@ -10,6 +10,8 @@
 //              exp2 / row sum / bf16 P written into the swizzled smem layout the UMMA descriptor expects),
 //              O stays in TMEM and is rescaled lazily (only when the running max grew by > 2^8, FA-style).
 // Scores never touch HBM; HBM traffic is Q + K + V + O once per (batch, head) (K/V re-reads hit L2).
+#include <type_traits>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -60,7 +62,7 @@ __device__ __forceinline__ void attn_tile_range(const AttnArgs& a, int b, int q0
 }
 
 template <int D>
-__global__ void __launch_bounds__(320, 2)
+__global__ void __launch_bounds__(320, (D == 128) ? 1 : 2)   // D = 128 is limited to one CTA per SM by shared memory anyway
 attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                  const __grid_constant__ CUtensorMap map_v, const AttnArgs a) {
     using Cfg = AttnCfg<D>;
@@ -289,37 +291,47 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 m_ref = m_new;
             }
             const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
-            // ---- pass 2: p = 2^(s*scale - m) -> bf16 P (swizzle block `half` of the K-major A tile), fp32 partial row sum
+            // ---- pass 2: p = 2^(s*scale - m) -> bf16 P (swizzle block `half` of the K-major A tile), fp32 partial row sum.
+            //      Two complete copies, masked / unmasked, chosen once per tile: with the `need_mask` test inside the element
+            //      loop the compiler emitted a branch + reconvergence pair around every element pair (ncu r01i source page:
+            //      BSSY / BRA / BSYNC x 32 per tile and thread, which also fenced the SFU results from overlapping).
             float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
             uint8_t* prow = sP + half * 16384 + row * 128;
+            auto pass2 = [&](auto masked_tag) {
+                constexpr bool MASKED = decltype(masked_tag)::value;
 #pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-                uint32_t v[32];
-                tmem_ld32(s_col + hh * 32, v);
-                tmem_ld_wait();
-                uint32_t pk[16];
+                for (int hh = 0; hh < 2; ++hh) {
+                    uint32_t v[32];
+                    tmem_ld32(s_col + hh * 32, v);
+                    tmem_ld_wait();
+                    uint32_t pk[16];
 #pragma unroll
-                for (int e = 0; e < 32; e += 2) {
-                    float p0 = fast_exp2(fmaf(__uint_as_float(v[e]), sl2, neg_m));
-                    float p1 = fast_exp2(fmaf(__uint_as_float(v[e + 1]), sl2, neg_m));
-                    if (need_mask) {
-                        p0 = (static_cast<uint32_t>(cbase + hh * 32 + e - vlo) <= vspan && !row_empty) ? p0 : 0.f;
-                        p1 = (static_cast<uint32_t>(cbase + hh * 32 + e + 1 - vlo) <= vspan && !row_empty) ? p1 : 0.f;
+                    for (int e = 0; e < 32; e += 2) {
+                        float p0 = fast_exp2(fmaf(__uint_as_float(v[e]), sl2, neg_m));
+                        float p1 = fast_exp2(fmaf(__uint_as_float(v[e + 1]), sl2, neg_m));
+                        if (MASKED) {
+                            p0 = (static_cast<uint32_t>(cbase + hh * 32 + e - vlo) <= vspan && !row_empty) ? p0 : 0.f;
+                            p1 = (static_cast<uint32_t>(cbase + hh * 32 + e + 1 - vlo) <= vspan && !row_empty) ? p1 : 0.f;
+                        }
+                        if (e & 2) {
+                            l2 += p0;
+                            l3 += p1;
+                        } else {
+                            l0 += p0;
+                            l1 += p1;
+                        }
+                        pk[e >> 1] = pack_bf16x2(p0, p1);
                     }
-                    if (e & 2) {
-                        l2 += p0;
-                        l3 += p1;
-                    } else {
-                        l0 += p0;
-                        l1 += p1;
-                    }
-                    pk[e >> 1] = pack_bf16x2(p0, p1);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g)
+                        *reinterpret_cast<uint4*>(prow + (((hh * 4 + g) ^ (row & 7)) << 4)) =
+                            make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
                 }
-#pragma unroll
-                for (int g = 0; g < 4; ++g)
-                    *reinterpret_cast<uint4*>(prow + (((hh * 4 + g) ^ (row & 7)) << 4)) =
-                        make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-            }
+            };
+            if (need_mask)
+                pass2(std::true_type{});
+            else
+                pass2(std::false_type{});
             l_run = l_run * alpha + ((l0 + l1) + (l2 + l3));
             fence_proxy_async_smem();
             tc_fence_before();
