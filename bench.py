@@ -156,9 +156,20 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
 
-        # NCCL writes its version banner / debug lines to stdout by default; stdout carries the ONE JSON line of the contract
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner straight to file descriptor 1 when the first communicator comes up (NCCL_DEBUG_FILE
+        # does not move it); stdout carries the ONE JSON line of the contract, so fd 1 points at stderr while the communicator
+        # is created (init + one barrier) and is restored afterwards.
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     from audio_flamingo_b200 import AF3FeatureExtractor, AudioFlamingo3ForConditionalGeneration, ops
     from audio_flamingo_b200.sharding import gather_tokens
 
