@@ -115,7 +115,10 @@ int af3_gemm_qkv_rope(void* stream, const void* x, int ldx, const void* w, int l
                       const int* pos_dev, void* workspace, size_t workspace_bytes);
 
 /* Single-token attention over the KV cache (decode step; SDPA:40-104 with q_len = 1).  ctx_len is read from device
- * memory so the launch can live in a CUDA graph.  q at qkv (packed [B, (H+2Hkv)*D]); out [B, H*D]. */
+ * memory so the launch can live in a CUDA graph.  q at qkv (packed [B, (H+2Hkv)*D]); out [B, H*D].
+ * scratch: af3_decode_attention_scratch_bytes() bytes, ZERO on first use (it holds the split arrival counters, which the
+ * kernel leaves at zero).  Cache rows at or beyond ctx_len are read and multiplied by P = 0: they must hold finite values
+ * (allocate the cache zero-initialised).  Requires ctx_len > kv_start[b] for every sequence. */
 int af3_decode_attention(void* stream, const void* qkv, const void* k_cache, const void* v_cache, void* out,
                          float* scratch, int B, int H, int Hkv, int D, int Tmax, const int* ctx_len,
                          const int* kv_start, float scale);
