@@ -100,3 +100,23 @@ def test_model_refuses_cpu():
     enc = AudioFlamingo3Encoder(O.hf_config("tiny").audio_config)
     with pytest.raises(AF3Error, match="no CPU fallback"):
         enc(torch.zeros(1, 128, 3000), torch.ones(1, 3000, dtype=torch.int32))
+
+
+def test_kv_cache_reset_restores_fresh_state():
+    """generate() reuses one AF3KVCache (and the decode graph captured over its buffers) for successive prompts: reset() must
+    give back the state of a fresh cache -- zero rows, zero left-padding, position 0 -- in the SAME storages."""
+    import torch
+
+    from audio_flamingo_b200.modeling import AF3KVCache
+
+    c = AF3KVCache(n_layers=2, B=3, Hkv=2, Tmax=8, D=4, device="cpu")
+    ptrs = (c.k.data_ptr(), c.v.data_ptr(), c.kv_start.data_ptr(), c.pos_dev.data_ptr(), c.ctx_dev.data_ptr())
+    c.k.fill_(1.5), c.v.fill_(float("inf"))      # whatever an earlier prompt left behind, finite or not
+    c.kv_start.copy_(torch.tensor([0, 2, 5], dtype=torch.int32))
+    c.length = 7
+    c.pos_dev.fill_(7), c.ctx_dev.fill_(8)
+    c.reset()
+    assert (c.k.data_ptr(), c.v.data_ptr(), c.kv_start.data_ptr(), c.pos_dev.data_ptr(), c.ctx_dev.data_ptr()) == ptrs
+    assert c.length == 0 and c.get_seq_length() == 0
+    assert not c.k.any() and not c.v.any() and not c.kv_start.any()
+    assert int(c.pos_dev) == 0 and int(c.ctx_dev) == 1
