@@ -120,3 +120,28 @@ def test_kv_cache_reset_restores_fresh_state():
     assert c.length == 0 and c.get_seq_length() == 0
     assert not c.k.any() and not c.v.any() and not c.kv_start.any()
     assert int(c.pos_dev) == 0 and int(c.ctx_dev) == 1
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the driver's reference arm; CPU only) must print exactly one JSON line carrying the contract
+    keys, on the same metric / unit / config.workload as our arm."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [ln for ln in p.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    import bench
+
+    assert d["impl"] == "reference" and d["metric"] == bench.METRIC and d["unit"] == "tokens/s" and d["higher_is_better"] is True
+    assert d["config"]["workload"] == bench.WORKLOAD and d["value"] > 0 and d["steps"] == 1
+    assert d["e2e"] == {"value": d["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "reference" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["dtype"] in ("bf16", "fp32")
+    assert set(cb["dtype_probe_ms"]) == {"bf16", "fp32"} and "cpu_model" in cb["host"] and "sample" in cb
