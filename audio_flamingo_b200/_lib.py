@@ -19,6 +19,10 @@ SIGNATURES = {
     "af3_last_error": (C.c_char_p, []),
     "af3_abi_version": (_i, []),
     "af3_set_pdl": (None, [_i]),
+    "af3_trace_slot_bytes": (_sz, []),
+    "af3_trace_begin": (_i, [_p, _sz]),
+    "af3_trace_end": (_i, []),
+    "af3_trace_seq": (_i, []),
     "af3_gemm_bf16": (_i, [_p, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _p, _p, _i, _i]),
     "af3_gemm_workspace_bytes": (_sz, []),
     "af3_gemm_bf16_ws": (_i, [_p, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p, _sz]),

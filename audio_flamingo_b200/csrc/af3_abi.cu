@@ -19,6 +19,9 @@ int rotary_time(cudaStream_t stream, bf16* x, const float* ts, const float* inv_
                 float window_duration, float max_len);
 int rope_table(cudaStream_t stream, float* cs, int B, int D, const int* pos_dev, const int* kv_start, const float* inv_freq);
 size_t gemm_workspace_bytes();
+int trace_begin(void* buf, size_t bytes);
+int trace_end();
+int trace_seq();
 int logmel(cudaStream_t stream, const float* wave, int n_win, int n_samples, const float* hann, const float* table,
            const float* filt, const int* klo, const int* khi, float* out, int* win_max);
 int layernorm(cudaStream_t, const bf16*, bf16*, const bf16*, const bf16*, int, int, float);
@@ -52,6 +55,10 @@ extern "C" {
 const char* af3_last_error(void) { return af3::last_error_cstr(); }
 int af3_abi_version(void) { return 1; }
 void af3_set_pdl(int enable) { af3::set_pdl(enable != 0); }
+size_t af3_trace_slot_bytes(void) { return sizeof(unsigned long long) * af3::TRACE_CTAS * af3::TRACE_MARKS; }
+int af3_trace_begin(void* buf, size_t bytes) { return af3::trace_begin(buf, bytes); }
+int af3_trace_end(void) { return af3::trace_end(); }
+int af3_trace_seq(void) { return af3::trace_seq(); }
 
 int af3_gemm_bf16(void* stream, const void* x, int ldx, const void* w, int ldw, void* out, int ldo, int n_tok, int n_feat,
                   int K, int flags, const void* bias, const void* resid, int ld_res, int res_period) {

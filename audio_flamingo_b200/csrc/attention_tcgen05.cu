@@ -382,10 +382,9 @@ static int launch_attention(cudaStream_t stream, const CUtensorMap& mq, const CU
                             const AttnArgs& a, int B) {
     using Cfg = AttnCfg<D>;
     auto kern = attention_kernel<D>;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce once;
+    if (once.first()) {
         AF3_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        configured = true;
     }
     dim3 grid(ceil_div(a.Tq, AT_BM), a.H, B);
     kern<<<grid, 320, Cfg::SMEM_BYTES, stream>>>(mq, mk, mv, a);

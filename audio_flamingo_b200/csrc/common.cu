@@ -69,15 +69,46 @@ static bool g_pdl = false;
 bool pdl_enabled() { return g_pdl; }
 void set_pdl(bool on) { g_pdl = on; }
 
-int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
-    }
+// ---- in-graph timeline (see common.h)
+static unsigned long long* g_trace_buf = nullptr;
+static size_t g_trace_slots = 0;
+static int g_trace_seq = 0;
+int trace_begin(void* buf, size_t bytes) {
+    g_trace_buf = static_cast<unsigned long long*>(buf);
+    g_trace_slots = bytes / (sizeof(unsigned long long) * TRACE_CTAS * TRACE_MARKS);
+    g_trace_seq = 0;
+    return 0;
+}
+int trace_end() {
+    const int n = g_trace_seq;
+    g_trace_buf = nullptr;
+    g_trace_slots = 0;
     return n;
+}
+int trace_seq() { return g_trace_seq; }
+unsigned long long* trace_next_slot() {
+    if (!g_trace_buf) return nullptr;
+    if (static_cast<size_t>(g_trace_seq) >= g_trace_slots) {
+        ++g_trace_seq;  // counted, not recorded
+        return nullptr;
+    }
+    return g_trace_buf + static_cast<size_t>(g_trace_seq++) * TRACE_CTAS * TRACE_MARKS;
+}
+
+int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev;
+}
+
+int sm_count() {
+    static int n[128] = {0};
+    const int dev = current_device() & 127;
+    if (n[dev] == 0) {
+        cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+        if (n[dev] <= 0) n[dev] = 148;
+    }
+    return n[dev];
 }
 
 }  // namespace af3

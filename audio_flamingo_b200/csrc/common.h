@@ -38,7 +38,21 @@ int make_tmap_2d(CUtensorMap* map, const void* base, uint64_t cols, uint64_t row
 int make_tmap_3d(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t p1_elems,
                  uint64_t p2_elems, uint32_t box0, uint32_t box1, uint32_t box2);
 
-int sm_count();
+int sm_count();        // of the CURRENT device (cached per device ordinal)
+int current_device();
+
+// One-time per-DEVICE kernel setup (cudaFuncSetAttribute is per device): a model on cuda:1 after one on cuda:0 in the
+// same process must configure its kernels again.  Usage: static DeviceOnce once; if (once.first()) {...}
+struct DeviceOnce {
+    unsigned long long mask[2] = {0, 0};  // device ordinals 0..127
+    bool first() {
+        const int d = current_device() & 127;
+        const unsigned long long bit = 1ull << (d & 63);
+        if (mask[d >> 6] & bit) return false;
+        mask[d >> 6] |= bit;
+        return true;
+    }
+};
 
 // Programmatic dependent launch for the decode-step kernel chain (af3_set_pdl).  launch_kernel() adds the
 // cudaLaunchAttributeProgrammaticStreamSerialization attribute when enabled; every kernel launched through it calls
@@ -63,5 +77,14 @@ inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, 
 }
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// In-graph timeline of the decode-step kernel chain (af3_trace_begin / af3_trace_end, profiles/decode_timeline.py).
+// While a trace is open every launch of an instrumented kernel gets the next slot of TRACE_CTAS x TRACE_MARKS
+// %globaltimer stamps in the caller's device buffer (the slot address is baked into the launch, so a captured CUDA
+// graph keeps writing the same slots on every replay: the buffer then holds the timeline of the LAST replay, with
+// programmatic dependent launch on and nothing serialised -- what ncu cannot show).  nullptr = tracing off.
+constexpr int TRACE_CTAS = 160;   // CTAs recorded per launch (linear block index below this)
+constexpr int TRACE_MARKS = 4;    // 0 entry, 1 after griddepcontrol.wait, 2 main loop done, 3 exit
+unsigned long long* trace_next_slot();
 
 }  // namespace af3

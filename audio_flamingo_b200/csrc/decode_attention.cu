@@ -30,12 +30,14 @@ namespace af3 {
 
 constexpr int DA_CHUNK = 128;    // keys per ring stage
 constexpr int DA_NH = 16;        // query heads per KV head, padded (UMMA N)
-constexpr int DA_NS = 3;         // K/V ring stages
+constexpr int DA_NS_MAX = 3;     // K/V ring stages (template parameter NS: 2 or 3)
 constexpr int DA_THREADS = 192;  // warps 0-3: softmax / accumulate (thread = TMEM lane), warp 4: MMA issue, warp 5: TMA
 constexpr int DA_D = 128;
 constexpr int DA_STAGE = 2 * DA_CHUNK * DA_D * 2;  // K tile + V tile
-constexpr int DA_SMEM = DA_NS * DA_STAGE + 2 * (DA_NH * 128) /*Q: 2 blocks of 16 x 128 B*/ +
-                        2 * 2 * (DA_NH * 128) /*P, double-buffered*/ + 1024 /*align*/ + 2048 /*barriers + reduction scratch*/;
+constexpr int da_smem(int ns) {
+    return ns * DA_STAGE + 2 * (DA_NH * 128) /*Q: 2 blocks of 16 x 128 B*/ + 2 * 2 * (DA_NH * 128) /*P, double-buffered*/ +
+           1024 /*align*/ + 2048 /*barriers + reduction scratch*/;
+}
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
@@ -105,24 +107,25 @@ __device__ __forceinline__ float da_exp2(float x) {
 // NG = query heads handled per thread (8 when G <= 8, else 16).  The per-head loops are branch-free over NG so the NG
 // independent shuffle / SFU chains interleave: with one CTA per SM each softmax warp is alone on its scheduler and every
 // dependent-instruction latency is otherwise exposed (ncu r01b: 90 % of the softmax warps' samples sat in those chains).
-template <int NG>
+template <int NG, int DA_NS>
 __global__ void __launch_bounds__(DA_THREADS, 1)
 decode_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                    const __grid_constant__ CUtensorMap map_v, float* __restrict__ part, bf16* __restrict__ out,
                    int* __restrict__ counters, int H, int Hkv, int nz, const int* __restrict__ ctx_len_p,
-                   const int* __restrict__ kv_start, float scale_log2) {
+                   const int* __restrict__ kv_start, float scale_log2, unsigned long long* trace) {
     constexpr int D = DA_D;
     const int G = H / Hkv;
     const int b = blockIdx.x, hk = blockIdx.y, sp = blockIdx.z;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) trace_mark(trace, 0);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sKV = smem;                         // DA_NS stages of {K: 2 blocks [128 keys x 128 B], V: same}
     uint8_t* sQ = sKV + DA_NS * DA_STAGE;        // 2 blocks [16 heads x 128 B]
     uint8_t* sP = sQ + 2 * DA_NH * 128;          // 2 buffers x 2 blocks [16 heads x 128 B]  (64 keys along each 128-byte row)
     uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * DA_NH * 128);
-    uint64_t *q_full = bars, *k_full = bars + 1, *v_full = k_full + DA_NS, *kv_empty = v_full + DA_NS,
-             *s_full = kv_empty + DA_NS, *p_full = s_full + 2, *o_full = p_full + 2;
+    uint64_t *q_full = bars, *k_full = bars + 1, *v_full = k_full + DA_NS_MAX, *kv_empty = v_full + DA_NS_MAX,
+             *s_full = kv_empty + DA_NS_MAX, *p_full = s_full + 2, *o_full = p_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
     float* red = reinterpret_cast<float*>(bars) + 256;  // [2 parities][4 warps][16 heads] chunk maxima, then [4][16] sums
     __shared__ int last_flag;
@@ -155,6 +158,7 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     const uint32_t tmem_S = *tmem_slot, tmem_O = tmem_S + 2 * DA_NH;  // S0 S1 O0 O1, 16 columns each
     pdl_launch_dependents();
     pdl_wait();
+    if (tid == 0) trace_mark(trace, 1);
 
     // ---- this CTA's share of the live chunks
     const int ctx = *ctx_len_p;
@@ -307,6 +311,7 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 if (i >= 1) accumulate(i - 1, m_pp, m_prev);
             }
             accumulate(n - 1, m_prev, m_run);
+            if (tid == 0) trace_mark(trace, 2);
             // ---- softmax denominators: sum the per-thread partial sums over the 128 key lanes
             float* reds = red + 128;
 #pragma unroll
@@ -343,12 +348,16 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     if (nz > 1) __threadfence();  // partials visible before this split is counted
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_S, 64);
-    if (nz == 1) return;
+    if (nz == 1) {
+        if (tid == 0) trace_mark(trace, 3);
+        return;
+    }
     // ---- the last-arriving split CTA of this (sequence, KV head) merges all split partials (log-sum-exp combine):
     //      replaces a separate combine kernel per layer
     if (tid == 0) last_flag = (atomicAdd(counters + b * Hkv + hk, 1) == nz - 1);
     __syncthreads();
     if (last_flag) combine_heads(part, out, counters, b, hk, G, H, Hkv, nz, 0, n_used);
+    if (tid == 0) trace_mark(trace, 3);
 }
 
 static int n_chunks(int Tmax) { return ceil_div(Tmax, DA_CHUNK); }
@@ -381,11 +390,15 @@ int decode_attention(cudaStream_t stream, const bf16* qkv, const bf16* k_cache, 
     AF3_REQUIRE(ctx_len != nullptr, "decode_attention: ctx_len must be a device pointer");
     AF3_REQUIRE(Hkv <= 65535, "decode_attention: too many KV heads");
     const int nz = pick_splits(B, Hkv, Tmax);
-    static bool configured = false;
-    if (!configured) {
-        AF3_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, DA_SMEM));
-        AF3_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, DA_SMEM));
-        configured = true;
+    // ring depth: 3 stages (192 KB in flight) or 2 (128 KB), the latter so that the kernel can be co-resident with a
+    // few-token GEMM of the decode chain under programmatic dependent launch (AF3_DA_STAGES, experiments)
+    static const int ns = [] { const char* e = getenv("AF3_DA_STAGES"); const int v = e ? atoi(e) : 3; return v == 2 ? 2 : 3; }();
+    static DeviceOnce once;
+    if (once.first()) {
+        AF3_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, da_smem(2)));
+        AF3_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, da_smem(2)));
+        AF3_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_kernel<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, da_smem(3)));
+        AF3_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_kernel<16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, da_smem(3)));
     }
     CUtensorMap mq, mk, mv;
     // q heads as rows of 128: the packed projection row of sequence b holds (H + 2 Hkv) such rows
@@ -398,9 +411,10 @@ int decode_attention(cudaStream_t stream, const bf16* qkv, const bf16* k_cache, 
         return e;
     dim3 grid(B, Hkv, nz);
     int* counters = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(scratch) + partial_bytes(B, H, D, Tmax));
-    auto kern = (H / Hkv <= 8) ? decode_attn_kernel<8> : decode_attn_kernel<16>;
-    AF3_CHECK_CUDA(launch_kernel(kern, grid, dim3(DA_THREADS), DA_SMEM, stream, mq, mk, mv, scratch, out, counters, H, Hkv, nz,
-                                 ctx_len, kv_start, scale * 1.4426950408889634f));
+    auto kern = (H / Hkv <= 8) ? (ns == 2 ? decode_attn_kernel<8, 2> : decode_attn_kernel<8, 3>)
+                               : (ns == 2 ? decode_attn_kernel<16, 2> : decode_attn_kernel<16, 3>);
+    AF3_CHECK_CUDA(launch_kernel(kern, grid, dim3(DA_THREADS), da_smem(ns), stream, mq, mk, mv, scratch, out, counters, H, Hkv, nz,
+                                 ctx_len, kv_start, scale * 1.4426950408889634f, trace_next_slot()));
     return 0;
 }
 

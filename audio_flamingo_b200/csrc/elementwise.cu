@@ -132,9 +132,11 @@ int avgpool_layernorm(cudaStream_t stream, const bf16* x, bf16* y, const bf16* g
 template <int NV>
 __global__ void __launch_bounds__(256)
 rmsnorm_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const bf16* __restrict__ weight, int rows, int dim,
-               float eps, const int* __restrict__ row_idx) {
+               float eps, const int* __restrict__ row_idx, unsigned long long* trace) {
+    if (threadIdx.x == 0) trace_mark(trace, 0);
     pdl_launch_dependents();
     pdl_wait();
+    if (threadIdx.x == 0) trace_mark(trace, 1);
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -166,15 +168,18 @@ rmsnorm_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const bf16* __r
             yp[c] = pack8(o);
         }
     }
+    if (threadIdx.x == 0) trace_mark(trace, 3);
 }
 
 // Few rows (decode step: 32 tokens): one CTA of 256 threads per row, so a 7 KB row is a single round of 16-byte loads
 // per thread instead of 14 dependent-latency rounds in one warp.
 __global__ void __launch_bounds__(256)
 rmsnorm_rowblock_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const bf16* __restrict__ weight, int dim, float eps,
-                        const int* __restrict__ row_idx) {
+                        const int* __restrict__ row_idx, unsigned long long* trace) {
+    if (threadIdx.x == 0) trace_mark(trace, 0);
     pdl_launch_dependents();
     pdl_wait();
+    if (threadIdx.x == 0) trace_mark(trace, 1);
     const int row = blockIdx.x;
     const size_t in_row = row_idx ? static_cast<size_t>(row_idx[row]) : static_cast<size_t>(row);
     const int nchunk = dim >> 3;
@@ -212,6 +217,7 @@ rmsnorm_rowblock_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const 
             yp[c] = pack8(o);
         }
     }
+    if (threadIdx.x == 0) trace_mark(trace, 3);
 }
 
 int rmsnorm(cudaStream_t stream, const bf16* x, bf16* y, const bf16* weight, int rows, int dim, float eps,
@@ -219,16 +225,17 @@ int rmsnorm(cudaStream_t stream, const bf16* x, bf16* y, const bf16* weight, int
     AF3_REQUIRE(dim % 8 == 0 && dim <= NORM_MAXV * 256, "rmsnorm: dim must be a multiple of 8 and <= 4096");
     if (rows <= 0) return 0;
     if (rows <= 1024) {
-        AF3_CHECK_CUDA(launch_kernel(rmsnorm_rowblock_kernel, dim3(rows), dim3(256), 0, stream, x, y, weight, dim, eps, row_idx));
+        AF3_CHECK_CUDA(launch_kernel(rmsnorm_rowblock_kernel, dim3(rows), dim3(256), 0, stream, x, y, weight, dim, eps, row_idx, trace_next_slot()));
         return 0;
     }
     const int need = ceil_div(dim >> 3, 32);
+    unsigned long long* tr = trace_next_slot();
     if (need <= 5)
-        AF3_CHECK_CUDA(launch_kernel(rmsnorm_kernel<5>, dim3(ceil_div(rows, 8)), dim3(256), 0, stream, x, y, weight, rows, dim, eps, row_idx));
+        AF3_CHECK_CUDA(launch_kernel(rmsnorm_kernel<5>, dim3(ceil_div(rows, 8)), dim3(256), 0, stream, x, y, weight, rows, dim, eps, row_idx, tr));
     else if (need <= 14)
-        AF3_CHECK_CUDA(launch_kernel(rmsnorm_kernel<14>, dim3(ceil_div(rows, 8)), dim3(256), 0, stream, x, y, weight, rows, dim, eps, row_idx));
+        AF3_CHECK_CUDA(launch_kernel(rmsnorm_kernel<14>, dim3(ceil_div(rows, 8)), dim3(256), 0, stream, x, y, weight, rows, dim, eps, row_idx, tr));
     else
-        AF3_CHECK_CUDA(launch_kernel(rmsnorm_kernel<16>, dim3(ceil_div(rows, 8)), dim3(256), 0, stream, x, y, weight, rows, dim, eps, row_idx));
+        AF3_CHECK_CUDA(launch_kernel(rmsnorm_kernel<16>, dim3(ceil_div(rows, 8)), dim3(256), 0, stream, x, y, weight, rows, dim, eps, row_idx, tr));
     return 0;
 }
 
@@ -367,6 +374,7 @@ rope_kv_append_kernel(bf16* __restrict__ qkv, bf16* __restrict__ k_cache, bf16* 
         const int b = static_cast<int>(bt / T);
         const int d0 = ch * 8;
         const int cpos = p0 + t;  // cache slot
+        if (cpos >= Tmax) continue;  // never past the allocation (device-side position: the host cannot check it)
         bf16* tok = qkv + static_cast<size_t>(bt) * heads * D;
         const int h_beg = HEAD_PAR ? h_only : 0, h_end = HEAD_PAR ? h_only + 1 : heads;
         if (h_beg < H + Hkv) {
@@ -473,9 +481,11 @@ int rotary_time(cudaStream_t stream, bf16* x, const float* ts, const float* inv_
 // cos/sin table of ONE decode step for the RoPE-fused q/k/v projection epilogue: cs[b][i] = (bf16(cos), bf16(sin)) of
 // inv_freq[i] * position(b), position = slot - kv_start[b] (Q2M:100-113; identical for all layers of the step).
 __global__ void rope_table_kernel(float2* __restrict__ cs, int B, int half, const int* __restrict__ pos_dev,
-                                  const int* __restrict__ kv_start, const float* __restrict__ inv_freq) {
+                                  const int* __restrict__ kv_start, const float* __restrict__ inv_freq, unsigned long long* trace) {
+    if (threadIdx.x == 0) trace_mark(trace, 0);
     pdl_launch_dependents();
     pdl_wait();
+    if (threadIdx.x == 0) trace_mark(trace, 1);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * half) return;
     const int b = i / half, d = i - b * half;
@@ -483,6 +493,7 @@ __global__ void rope_table_kernel(float2* __restrict__ cs, int B, int half, cons
     if (pos < 0) pos = 1;
     const float fr = inv_freq[d] * static_cast<float>(pos);
     cs[i] = make_float2(bf16_round(cosf(fr)), bf16_round(sinf(fr)));
+    if (threadIdx.x == 0) trace_mark(trace, 3);
 }
 
 int rope_table(cudaStream_t stream, float* cs, int B, int D, const int* pos_dev, const int* kv_start, const float* inv_freq) {
@@ -490,7 +501,7 @@ int rope_table(cudaStream_t stream, float* cs, int B, int D, const int* pos_dev,
     const int n = B * (D / 2);
     if (n <= 0) return 0;
     AF3_CHECK_CUDA(launch_kernel(rope_table_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, stream, reinterpret_cast<float2*>(cs), B,
-                                 D / 2, pos_dev, kv_start, inv_freq));
+                                 D / 2, pos_dev, kv_start, inv_freq, trace_next_slot()));
     return 0;
 }
 
@@ -500,12 +511,15 @@ int rope_table(cudaStream_t stream, float* cs, int B, int D, const int* pos_dev,
 // token; exclusive scan of post_len -> first ordinal of each window.  Kernel 2: one warp per token row copy.
 __global__ void __launch_bounds__(1024)
 scatter_index_kernel(const int64_t* __restrict__ ids, int n_tok, int64_t audio_id, const int* __restrict__ post_len,
-                     int n_win, int frames, int* __restrict__ src_row /*[n_tok]*/, int* __restrict__ counts) {
+                     int n_win, int frames, int* __restrict__ src_row /*[n_tok]*/, int* __restrict__ counts,
+                     unsigned long long* trace) {
     __shared__ int warp_tot[32];
     __shared__ int carry;
     __shared__ int win_base[1025];
+    if (threadIdx.x == 0) trace_mark(trace, 0);
     pdl_launch_dependents();
     pdl_wait();
+    if (threadIdx.x == 0) trace_mark(trace, 1);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // window prefix (n_win <= 1024 handled in one sweep; larger handled serially by thread 0)
     if (tid == 0) {
@@ -560,13 +574,17 @@ scatter_index_kernel(const int64_t* __restrict__ ids, int n_tok, int64_t audio_i
         __syncthreads();
     }
     if (tid == 0) counts[0] = carry;
+    if (tid == 0) trace_mark(trace, 3);
 }
 
 __global__ void __launch_bounds__(256)
 embed_scatter_kernel(const int64_t* __restrict__ ids, int n_tok, const bf16* __restrict__ table, int dim,
-                     const bf16* __restrict__ audio, const int* __restrict__ src_row, bf16* __restrict__ out) {
+                     const bf16* __restrict__ audio, const int* __restrict__ src_row, bf16* __restrict__ out,
+                     unsigned long long* trace) {
+    if (threadIdx.x == 0) trace_mark(trace, 0);
     pdl_launch_dependents();
     pdl_wait();
+    if (threadIdx.x == 0) trace_mark(trace, 1);
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= n_tok) return;
@@ -575,6 +593,7 @@ embed_scatter_kernel(const int64_t* __restrict__ ids, int n_tok, const bf16* __r
     const uint4* s4 = reinterpret_cast<const uint4*>(src);
     uint4* d4 = reinterpret_cast<uint4*>(out + static_cast<size_t>(row) * dim);
     for (int c = lane; c < dim / 8; c += 32) d4[c] = __ldg(s4 + c);
+    if (threadIdx.x == 0) trace_mark(trace, 3);
 }
 
 int embed_scatter(cudaStream_t stream, const int64_t* ids, int n_tok, const bf16* table, int dim, int64_t audio_id,
@@ -586,9 +605,9 @@ int embed_scatter(cudaStream_t stream, const int64_t* ids, int n_tok, const bf16
     static const int zero_len = 0;
     (void)zero_len;
     AF3_CHECK_CUDA(launch_kernel(scatter_index_kernel, dim3(1), dim3(1024), 0, stream, ids, n_tok, audio_id, post_len, n_win,
-                                 frames, src_row_scratch, counts));
+                                 frames, src_row_scratch, counts, trace_next_slot()));
     AF3_CHECK_CUDA(launch_kernel(embed_scatter_kernel, dim3(ceil_div(n_tok, 8)), dim3(256), 0, stream, ids, n_tok, table, dim,
-                                 audio, src_row_scratch, out));
+                                 audio, src_row_scratch, out, trace_next_slot()));
     return 0;
 }
 
@@ -606,9 +625,12 @@ __device__ __forceinline__ void argmax_merge(float& best, int& bi, float ob, int
 }
 
 __global__ void __launch_bounds__(256)
-argmax_partial_kernel(const float* __restrict__ logits, int V, float* __restrict__ pmax, int* __restrict__ pidx) {
+argmax_partial_kernel(const float* __restrict__ logits, int V, float* __restrict__ pmax, int* __restrict__ pidx,
+                      unsigned long long* trace) {
+    if (threadIdx.x == 0) trace_mark(trace, 0);
     pdl_launch_dependents();
     pdl_wait();
+    if (threadIdx.x == 0) trace_mark(trace, 1);
     const int row = blockIdx.x, sp = blockIdx.y;
     const float* p = logits + static_cast<size_t>(row) * V;
     const int per = ((V + AM_SPLIT - 1) / AM_SPLIT + 3) & ~3;  // slice length, multiple of 4
@@ -644,19 +666,24 @@ argmax_partial_kernel(const float* __restrict__ logits, int V, float* __restrict
         for (int w = 1; w < 8; ++w) argmax_merge(best, bi, sb[w], si[w]);
         pmax[row * AM_SPLIT + sp] = best;
         pidx[row * AM_SPLIT + sp] = bi;
+        trace_mark(trace, 3);
     }
 }
 
 __global__ void __launch_bounds__(32)
-argmax_final_kernel(const float* __restrict__ pmax, const int* __restrict__ pidx, int64_t* __restrict__ out) {
+argmax_final_kernel(const float* __restrict__ pmax, const int* __restrict__ pidx, int64_t* __restrict__ out,
+                    unsigned long long* trace) {
+    if (threadIdx.x == 0) trace_mark(trace, 0);
     pdl_launch_dependents();
     pdl_wait();
+    if (threadIdx.x == 0) trace_mark(trace, 1);
     const int row = blockIdx.x, lane = threadIdx.x;
     float best = pmax[row * AM_SPLIT + lane];
     int bi = pidx[row * AM_SPLIT + lane];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) argmax_merge(best, bi, __shfl_xor_sync(0xffffffffu, best, o), __shfl_xor_sync(0xffffffffu, bi, o));
     if (lane == 0) out[row] = (bi == 0x7fffffff) ? 0 : bi;
+    if (lane == 0) trace_mark(trace, 3);
 }
 
 size_t argmax_scratch_bytes(int B) { return static_cast<size_t>(B) * AM_SPLIT * (sizeof(float) + sizeof(int)); }
@@ -666,9 +693,9 @@ int argmax(cudaStream_t stream, const float* logits, int B, int V, int64_t* out,
     AF3_REQUIRE(scratch != nullptr, "argmax: scratch of af3_argmax_scratch_bytes(B) bytes required");
     float* pmax = static_cast<float*>(scratch);
     int* pidx = reinterpret_cast<int*>(pmax + static_cast<size_t>(B) * AM_SPLIT);
-    AF3_CHECK_CUDA(launch_kernel(argmax_partial_kernel, dim3(B, AM_SPLIT), dim3(256), 0, stream, logits, V, pmax, pidx));
+    AF3_CHECK_CUDA(launch_kernel(argmax_partial_kernel, dim3(B, AM_SPLIT), dim3(256), 0, stream, logits, V, pmax, pidx, trace_next_slot()));
     AF3_CHECK_CUDA(launch_kernel(argmax_final_kernel, dim3(B), dim3(32), 0, stream, static_cast<const float*>(pmax),
-                                 static_cast<const int*>(pidx), out));
+                                 static_cast<const int*>(pidx), out, trace_next_slot()));
     return 0;
 }
 

@@ -51,6 +51,7 @@ struct GemmArgs {
     int k_splits;
     float* ws;      // [tiles][k_splits][BN][128] fp32
     int* counters;  // [tiles], zero on entry, reset to zero by the reducing CTA
+    unsigned long long* trace;  // in-graph timeline slot of this launch (common.h) or nullptr
 };
 
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle atom row
@@ -117,6 +118,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) trace_mark(a.trace, 0);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_r);
@@ -246,6 +248,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
         const int row_in_tile = q * 32 + lane;
         const int flags = (EPI >= 0) ? EPI : a.flags;
         pdl_wait();  // residual reads / output writes / split-K workspace are ordered after every earlier kernel
+        if (threadIdx.x == 64) trace_mark(a.trace, 1);
         int acc = 0;
         uint32_t acc_phase = 0;
         uint32_t egrp = 0;             // running 64-column group counter of this warp (selects the staging buffer)
@@ -267,6 +270,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
             }
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
+            if (threadIdx.x == 64) trace_mark(a.trace, 2);
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * Cfg::ACC_COLS;
 
             if constexpr (!SWAP) {
@@ -546,14 +550,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
                                 const int head = r, q4 = et & 3;
                                 const uint4* tp = reinterpret_cast<const uint4*>(tile + (et >> 2) * 128 + q4 * 32);
                                 bf16* op;
+                                bool store = true;
                                 if (head < a.rope_H)
                                     op = reinterpret_cast<bf16*>(a.out) + static_cast<size_t>(tok) * a.ldo + f0;
                                 else {
                                     const int hk = (head - a.rope_H) % a.rope_Hkv;
                                     bf16* cache = (head < a.rope_H + a.rope_Hkv) ? a.k_cache : a.v_cache;
-                                    op = cache + ((static_cast<size_t>(tok) * a.rope_Hkv + hk) * a.rope_Tmax + *a.rope_pos) * 128 + q4 * 32;
+                                    const int slot = *a.rope_pos;
+                                    // a full cache must never be written past its allocation (the host raises before launching;
+                                    // this guards graph replays whose position lives on the device)
+                                    store = slot >= 0 && slot < a.rope_Tmax;
+                                    op = cache + ((static_cast<size_t>(tok) * a.rope_Hkv + hk) * a.rope_Tmax + (store ? slot : 0)) * 128 + q4 * 32;
                                 }
-                                if (head < a.rope_H + a.rope_Hkv) {
+                                if (!store) {
+                                } else if (head < a.rope_H + a.rope_Hkv) {
                                     const uint4* pp = reinterpret_cast<const uint4*>(tile + (et >> 2) * 128 + (q4 ^ 2) * 32);  // d +- 64
                                     const float2* cs = a.rope_cs + static_cast<size_t>(tok) * 64 + (q4 & 1) * 32;
                                     const float sgn = (q4 < 2) ? -1.f : 1.f;  // rotate_half: -x[d+64] for d < 64, +x[d-64] otherwise
@@ -651,6 +661,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
     if (!SWAP && warp >= 2 && lane == 0) bulk_wait_read<0>();  // staged tiles must be read out before smem goes away
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) trace_mark(a.trace, 3);
     if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
@@ -659,10 +670,9 @@ static int launch_epi(const CUtensorMap& mr, const CUtensorMap& mc, const CUtens
                   const GemmArgs& a, cudaStream_t stream) {
     using Cfg = GemmCfg<BN, NA, STAGES, SWAP>;
     auto kern = gemm_kernel<BN, NA, STAGES, SWAP, EPI, EW>;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce once;
+    if (once.first()) {
         AF3_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        configured = true;
     }
     const int tiles = a.num_r_tiles * a.num_c_tiles * (SWAP && a.k_splits > 1 ? a.k_splits : 1);
     const int grid = tiles < sm_count() ? tiles : sm_count();
@@ -746,9 +756,10 @@ int gemm_bf16(cudaStream_t stream, const bf16* x, int ldx, const bf16* w, int ld
     a.res_period = res_period;
     a.flags = flags;
     a.k_splits = 1;
+    a.trace = trace_next_slot();
     if (flags & EPI_ROPE) {
         AF3_REQUIRE(rope && rope->cs && rope->k_cache && rope->v_cache && rope->pos, "gemm: EPI_ROPE needs the rope arguments");
-        AF3_REQUIRE(n_tok <= 32 && n_feat == (rope->H + 2 * rope->Hkv) * 128 && (ldo % 8) == 0 && !(flags & (EPI_RESID | EPI_F32OUT | EPI_SWIGLU)),
+        AF3_REQUIRE(n_tok <= 64 && n_feat == (rope->H + 2 * rope->Hkv) * 128 && (ldo % 8) == 0 && !(flags & (EPI_RESID | EPI_F32OUT | EPI_SWIGLU)),
                     "gemm: EPI_ROPE is the few-token fused q/k/v projection with head_dim 128");
         a.rope_cs = reinterpret_cast<const float2*>(rope->cs);
         a.k_cache = rope->k_cache;
@@ -795,8 +806,17 @@ int gemm_bf16(cudaStream_t stream, const bf16* x, int ldx, const bf16* w, int ld
     a.group_r = 1;
     if (int e = make_tmap_2d(&mw, w, K, w_rows, ldw, BK, 128)) return e;
     if (int e = make_tmap_2d(&mx, x, K, n_tok, ldx, BK, BN)) return e;
+    // Few-token pipeline depth.  Under programmatic dependent launch the NEXT kernel of the decode chain can only become
+    // resident (and start its pre-wait weight prefetch) while this one still runs if both fit in one SM's 227 KB of
+    // shared memory: 4 x 20 KB (NA = 1) / 3 x 36 KB (NA = 2) stages keep 64 / 96 KB of weights in flight per SM -- above
+    // the ~45 KB that HBM latency x per-SM bandwidth needs -- and leave room for the successor.  AF3_SWAP_STAGES /
+    // AF3_SWAP_STAGES2 select the depth (experiments; the defaults are the measured optimum).
+    static const int st1 = [] { const char* e = getenv("AF3_SWAP_STAGES"); return e ? atoi(e) : 8; }();
+    static const int st2 = [] { const char* e = getenv("AF3_SWAP_STAGES2"); return e ? atoi(e) : 6; }();
     if (swiglu) {
         a.num_r_tiles = ceil_div(w_rows, 256);
+        if (st2 == 3 && flags == EPI_SWIGLU) return launch_epi<BN, 2, 3, true, EPI_SWIGLU>(mw, mx, mw, mw, a, stream);
+        if (st2 == 4 && flags == EPI_SWIGLU) return launch_epi<BN, 2, 4, true, EPI_SWIGLU>(mw, mx, mw, mw, a, stream);
         return launch<BN, 2, 6, true>(mw, mx, mw, mw, a, stream);
     }
     a.num_r_tiles = ceil_div(w_rows, 128);
@@ -816,6 +836,17 @@ int gemm_bf16(cudaStream_t stream, const bf16* x, int ldx, const bf16* w, int ld
             a.counters = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(workspace) + (8u << 20));
         }
     }
+#define AF3_SWAP1_CASE(ST)                                                                                          \
+    if (st1 == ST) {                                                                                                \
+        if (flags == EPI_RESID) return launch_epi<BN, 1, ST, true, EPI_RESID>(mw, mx, mw, mw, a, stream);           \
+        if (flags == (EPI_BIAS | EPI_ROPE)) return launch_epi<BN, 1, ST, true, EPI_BIAS | EPI_ROPE>(mw, mx, mw, mw, a, stream); \
+        if (flags == EPI_F32OUT) return launch_epi<BN, 1, ST, true, EPI_F32OUT>(mw, mx, mw, mw, a, stream);         \
+    }
+    AF3_SWAP1_CASE(3)
+    AF3_SWAP1_CASE(4)
+    AF3_SWAP1_CASE(5)
+    AF3_SWAP1_CASE(6)
+#undef AF3_SWAP1_CASE
     return launch<BN, 1, 8, true>(mw, mx, mw, mw, a, stream);
 }
 

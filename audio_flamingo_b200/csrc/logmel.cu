@@ -214,11 +214,10 @@ int logmel(cudaStream_t stream, const float* wave, int n_win, int n_samples, con
            const float* filt, const int* klo, const int* khi, float* out, int* win_max) {
     AF3_REQUIRE(n_win > 0 && n_samples >= NFFT && n_samples % HOP == 0, "logmel: n_samples must be a positive multiple of 160");
     const int n_frames = n_samples / HOP;  // torch.stft yields n_frames+1, the reference drops the last (WFE:150)
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce once;
+    if (once.first()) {
         AF3_CHECK_CUDA(cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)sizeof(LogmelSmem)));
-        configured = true;
     }
     logmel_init_max<<<ceil_div(n_win, 128), 128, 0, stream>>>(win_max, n_win);
     AF3_CHECK_LAUNCH();

@@ -65,6 +65,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// ---------------------------------------------------------------- in-graph timeline (common.h: trace_next_slot)
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// one thread per CTA calls this; slot == nullptr (tracing off) costs one predicated branch
+__device__ __forceinline__ void trace_mark(unsigned long long* slot, int mark) {
+    if (slot) {
+        const unsigned cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+        if (cta < 160u) slot[cta * 4 + mark] = globaltimer_ns();
+    }
+}
+
 // ---------------------------------------------------------------- proxy fences
 // generic-proxy smem writes -> visible to the async proxy (UMMA / TMA reads of smem)
 __device__ __forceinline__ void fence_proxy_async_smem() {

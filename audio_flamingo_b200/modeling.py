@@ -15,6 +15,7 @@ reference with model.to(torch.bfloat16).
 """
 from __future__ import annotations
 
+import functools
 import math
 import os
 import time
@@ -43,6 +44,21 @@ except Exception:  # pragma: no cover - minimal stand-ins with the same field na
         loss: Optional[torch.Tensor] = None
         logits: torch.Tensor = None
         past_key_values: object = None
+
+
+def _on_model_device(fn):
+    """Runs a public entry point with the model's GPU as the current CUDA device: the C ABI launches on the current device
+    (include/af3b200.h), so a model living on cuda:1 must not launch on cuda:0."""
+
+    @functools.wraps(fn)
+    def wrapped(self, *args, **kwargs):
+        dev = self.language_model.lm_head.weight.device
+        if dev.type != "cuda":
+            return fn(self, *args, **kwargs)  # _check_ready() raises the "no CPU fallback" error
+        with torch.cuda.device(dev):
+            return fn(self, *args, **kwargs)
+
+    return wrapped
 
 
 def _cfg_get(cfg, name, default=None):
@@ -249,6 +265,25 @@ class AF3KVCache:
     def get_seq_length(self, layer_idx=0):
         return self.length
 
+    @staticmethod
+    def bucket(n_rows: int) -> int:
+        """Capacity is kept at multiples of 256 rows (one decode graph per bucket, see generate())."""
+        return -(-max(int(n_rows), 1) // 256) * 256
+
+    def ensure_capacity(self, n_rows: int):
+        """Grow (re-allocate + copy the live rows) so that `n_rows` slots exist: what DynamicCache's grow-by-cat gives the
+        reference's callers for free ([O] CACHE:119-120).  Only the eager forward() path grows a cache; generate() sizes it
+        up front because a captured decode graph holds the buffers' addresses."""
+        if n_rows <= self.Tmax:
+            return
+        new_T = self.bucket(n_rows)
+        k = torch.zeros(self.k.shape[:3] + (new_T, self.k.shape[4]), device=self.k.device, dtype=bf16)
+        v = torch.zeros_like(k)
+        if self.length > 0:
+            k[:, :, :, : self.length].copy_(self.k[:, :, :, : self.length])
+            v[:, :, :, : self.length].copy_(self.v[:, :, :, : self.length])
+        self.k, self.v, self.Tmax = k, v, new_T
+
 
 class Qwen2ForCausalLM(nn.Module):
     """Decoder ([O] Q2M:332-487) on sm_100a kernels: RMSNorm, fused QKV GEMM (+bias), RoPE + in-place KV append,
@@ -304,17 +339,23 @@ class Qwen2ForCausalLM(nn.Module):
         H, Hkv, D = self.H, self.Hkv, self.D
         pos0 = cache.length
         rope_cs = None
-        if decode:
-            if B > 32:
-                raise AF3Error("the fused decode step handles at most 32 sequences per GPU (shard the batch)")
+        fused_qkv = decode and B <= 64  # few-token ("swapped") GEMM with RoPE + KV append in its epilogue
+        if fused_qkv:
             rope_cs = ops.rope_table(B, D, cache.pos_dev, cache.kv_start, self._inv_freq)
         for li, (l, (wqkv, bqkv, wgu)) in enumerate(zip(self.model.layers, self._packed)):
             y = ops.rmsnorm(h, l.input_layernorm.weight, self.eps)
             kc, vc = cache.k[li], cache.v[li]
             a = torch.empty((B * T, H * D), device=h.device, dtype=bf16)
             if decode:
-                # q/k/v projection with RoPE + KV append in the GEMM epilogue (rope table: once per step, below)
-                qkv = ops.qkv_rope_linear(y, wqkv, bqkv, kc, vc, H=H, Hkv=Hkv, D=D, rope_cs=rope_cs, pos_dev=cache.pos_dev)
+                if fused_qkv:
+                    # q/k/v projection with RoPE + KV append in the GEMM epilogue (rope table: once per step, above)
+                    qkv = ops.qkv_rope_linear(y, wqkv, bqkv, kc, vc, H=H, Hkv=Hkv, D=D, rope_cs=rope_cs, pos_dev=cache.pos_dev)
+                else:
+                    # more than 64 sequences per GPU: token-major tensor-core GEMM + the stand-alone RoPE / append kernel reading
+                    # the slot from device memory (graph replay)
+                    qkv = ops.linear(y, wqkv, bqkv)
+                    ops.rope_kv_append(qkv, kc, vc, B=B, T=1, H=H, Hkv=Hkv, D=D, pos0=0, inv_freq=self._inv_freq,
+                                       kv_start=cache.kv_start, pos0_dev=cache.pos_dev)
                 ops.decode_attention(qkv, kc, vc, a, scratch, B=B, H=H, Hkv=Hkv, D=D, ctx_len=cache.ctx_dev,
                                      kv_start=cache.kv_start, scale=D ** -0.5)
             else:
@@ -336,19 +377,26 @@ class Qwen2ForCausalLM(nn.Module):
 
     @torch.no_grad()
     def prefill(self, inputs_embeds, kv_start, cache: AF3KVCache, logits_to_keep=1):
-        """inputs_embeds [B,S,hid] bf16 (consumed in place), kv_start int32 [B]. -> fp32 logits [B, keep|S, V]."""
+        """inputs_embeds [B,S,hid] bf16 (consumed in place), kv_start int32 [B]. -> fp32 logits [B, keep|S, V].
+        The chunk is appended at cache.length (0 for a fresh prompt; > 0 for the next slice of a chunked prefill or a later chat turn:
+        RoPE positions, the causal offset and the left padding of the first chunk carry over)."""
         self._check_ready()
         B, S, _ = inputs_embeds.shape
+        if B != cache.B:
+            raise AF3Error(f"KV cache was allocated for {cache.B} sequences, got {B}")
         if cache.length + S > cache.Tmax:
-            raise AF3Error("KV cache too small for this prompt")
-        if kv_start is None:
-            cache.kv_start.zero_()
-        else:
-            cache.kv_start.copy_(kv_start)
+            raise AF3Error(f"KV cache too small for this prompt ({cache.length} + {S} > capacity {cache.Tmax})")
+        if cache.length == 0:  # a continuation chunk (chunked prefill, next turn) keeps the left padding of the first chunk
+            if kv_start is None:
+                cache.kv_start.zero_()
+            else:
+                cache.kv_start.copy_(kv_start)
         h = self._layers(inputs_embeds.view(B * S, self.hid), B, S, cache, decode=False)
         cache.length += S
         cache.pos_dev.fill_(cache.length)
         cache.ctx_dev.fill_(cache.length + 1)
+        if logits_to_keep == -1:  # an inner slice of a chunked prefill: only the cache is wanted
+            return None
         if logits_to_keep == 0:
             return self._head(h).view(B, S, self.vocab)
         if logits_to_keep != 1:
@@ -361,6 +409,8 @@ class Qwen2ForCausalLM(nn.Module):
         """One q_len = 1 step: token_embeds [B, hid] (in place) -> fp32 logits [B, V]; appends at cache.pos_dev.
         Graph-capturable: positions / context length are read from device memory and advanced on the device."""
         B = token_embeds.shape[0]
+        if cache.length + 1 > cache.Tmax:  # the fused q/k/v epilogue appends at slot `length`: never past the allocation
+            raise AF3Error(f"KV cache full ({cache.length} of {cache.Tmax} slots): cache.ensure_capacity() or a larger reserve is needed")
         h = self._layers(token_embeds, B, 1, cache, decode=True, scratch=scratch)
         logits = self._head(h)
         cache.pos_dev.add_(1)
@@ -390,6 +440,8 @@ class AudioFlamingo3ForConditionalGeneration(nn.Module):
         # ~230-node step graph costs the launching thread 0.05-0.3 s during which the GPU idles (r01 bench host-gap logs), and a
         # serving loop issues the same (batch, max length) shape over and over.  release_decode_state() frees it.
         self._decode_state = None
+        self._deferred = []       # input-validation verdicts still on the device (see _defer_check)
+        self.generation_config = None  # the reference model's GenerationConfig when built by from_reference(); generate() defaults
         self.stage_events = None  # bench instrumentation: when a list, (name, cuda event) is appended at stage boundaries
         self.stage_host_t = None  # ... and, when a list, (name, host perf_counter at enqueue time): GPU-bound vs launch-bound
 
@@ -407,6 +459,7 @@ class AudioFlamingo3ForConditionalGeneration(nn.Module):
         """Build from an instantiated reference model (weights are copied, cast to bf16)."""
         m = cls(ref_model.config)
         m.load_reference_state_dict(ref_model.state_dict(), device=device)
+        m.generation_config = getattr(ref_model, "generation_config", None)
         return m
 
     def load_reference_state_dict(self, sd, device="cuda"):
@@ -433,6 +486,7 @@ class AudioFlamingo3ForConditionalGeneration(nn.Module):
         return self.language_model.lm_head
 
     # ---- audio branch
+    @_on_model_device
     @torch.no_grad()
     def get_audio_features(self, input_features, input_features_mask, input_ids=None, **kwargs):
         """[O] AF3M:447-475: tower -> projector -> keep the first post_len frames of every window."""
@@ -458,17 +512,36 @@ class AudioFlamingo3ForConditionalGeneration(nn.Module):
         post = (((lens - 1) // 2 + 1) - 2) // 2 + 1
         return emb, W, Tp, post.to(torch.int32).contiguous()
 
-    @staticmethod
-    def _left_pad_starts(attention_mask, B, S, device):
+    # ---- input validation without host<->device round trips on the hot path
+    def _defer_check(self, flag, exc, message):
+        """`flag`: 0-dim device tensor, non-zero = invalid input.  Raised by _raise_deferred() at the end of the public call (one
+        sync after everything has been enqueued) instead of stalling the launch thread between encoder and prefill."""
+        self._deferred.append((flag, exc, message))
+
+    def _raise_deferred(self):
+        pending, self._deferred = self._deferred, []
+        for flag, exc, message in pending:
+            if bool(flag.item()):
+                raise exc(message() if callable(message) else message)
+
+    def _left_pad_starts(self, attention_mask, B, S, device):
+        """int32 [B] number of left-padding slots per row.  The kernels implement the reference processor's left padding
+        ([O] AF3P:44-47): every mask row must be 0...01...1.  A host mask (what the processor returns) is validated on the host;
+        a device mask is validated on the device and the verdict is read at the end of the call (_raise_deferred)."""
+        msg = "attention_mask must be left padded (zeros then ones), as the AF3 processor produces"
         if attention_mask is None:
             return torch.zeros((B,), device=device, dtype=torch.int32)
-        am = attention_mask.to(device)
+        if tuple(attention_mask.shape) != (B, S):
+            raise AF3Error(f"attention_mask must have shape {(B, S)}, got {tuple(attention_mask.shape)}")
+        am = attention_mask
         n_valid = am.sum(-1)
-        # the kernels implement the reference's left padding (AF3P:44-47): mask must be 0...01...1
-        expect = torch.arange(S, device=device)[None, :] >= (S - n_valid)[:, None]
-        if not torch.equal(am.bool(), expect):
-            raise AF3Error("attention_mask must be left padded (zeros then ones), as the AF3 processor produces")
-        return (S - n_valid).to(torch.int32).contiguous()
+        expect = torch.arange(S, device=am.device)[None, :] >= (S - n_valid)[:, None]
+        bad = (am.bool() != expect).any()
+        if am.is_cuda:
+            self._defer_check(bad, AF3Error, msg)
+        elif bool(bad):
+            raise AF3Error(msg)
+        return (S - n_valid).to(device=device, dtype=torch.int32).contiguous()
 
     @torch.no_grad()
     def _prompt_embeds(self, input_ids, input_features, input_features_mask):
@@ -479,115 +552,227 @@ class AudioFlamingo3ForConditionalGeneration(nn.Module):
         if input_features is not None:
             emb, W, Tp, post = self._audio_embeds_raw(input_features.to(dev), input_features_mask.to(dev), input_ids.to(dev))
             x, counts = ops.embed_scatter(ids, table, self.config.audio_token_id, emb, W, Tp, post)
-            n_tok, n_feat = counts.tolist()
-            if n_tok != n_feat:  # masked_scatter would fail the same way (AF3M:564)
-                raise ValueError(f"Audio features and audio tokens do not match: tokens {n_tok}, features {n_feat}")
+            # masked_scatter would fail the same way (AF3M:564); a mismatch is memory-safe here (surplus placeholders keep their
+            # token embedding, surplus features are dropped), so the verdict is read at the end of the call
+            self._defer_check(counts[0] != counts[1], ValueError,
+                              lambda c=counts: "Audio features and audio tokens do not match: tokens {}, features {}".format(*c.tolist()))
         else:
             x, _ = ops.embed_scatter(ids, table, -1, None, 0, 1, None)
         return x.view(B, S, -1)
 
     # ---- forward ([O] AF3M:479-578)
+    @_on_model_device
     @torch.no_grad()
     def forward(self, input_ids=None, input_features=None, input_features_mask=None, attention_mask=None,
                 position_ids=None, past_key_values=None, inputs_embeds=None, labels=None, use_cache=None,
-                logits_to_keep=0, **kwargs):
+                logits_to_keep=0, reserve_tokens=None, **kwargs):
+        """Same call surface as the reference.  Three cases:
+          * no cache, or an empty one: prompt prefill (audio rows scattered into the prompt, AF3M:556-566);
+          * live cache + exactly one new token per sequence: one cached decode step (AF3M:580-592: no audio after the first pass);
+          * live cache + a longer chunk (next chat turn, optionally with new audio; one slice of a chunked prefill, GEN:3770-3806):
+            the chunk is appended at the cache's current length.  Its attention_mask -- [B, chunk] or the reference's
+            full-length [B, past + chunk] -- must be all ones over the chunk (the kernels keep one contiguous live range per row).
+        With use_cache the returned AF3KVCache has room for `reserve_tokens` more slots (default: up to the next multiple of 256)
+        and grows on demand in later calls, like DynamicCache."""
         if labels is not None:
             raise AF3Error("training (labels) is out of scope of the inference hot path")
         if position_ids is not None:
             raise AF3Error("explicit position_ids are not supported; they are derived from the left-padded attention_mask")
+        if (input_ids is None) == (inputs_embeds is None):
+            raise ValueError("You must specify exactly one of input_ids or inputs_embeds")      # AF3M:548
         self.language_model._check_ready()
         lm = self.language_model
         dev = lm.lm_head.weight.device
-        if past_key_values is not None and past_key_values.length > 0:
-            # cached continuation: only the new token(s) are passed (AF3M:580-592: no audio after the first iteration)
-            if input_ids is None or input_ids.shape[1] != 1:
-                raise AF3Error("cached forward expects exactly one new token per sequence")
-            B = input_ids.shape[0]
-            x, _ = ops.embed_scatter(input_ids.to(dev).reshape(-1).contiguous(), lm.model.embed_tokens.weight, -1, None, 0, 1, None)
-            scratch = ops.decode_attention_scratch(B, lm.H, lm.D, past_key_values.Tmax, dev)
-            logits = lm.decode_step(x, past_key_values, scratch)
-            past_key_values.length += 1
-            return CausalLMOutputWithPast(logits=logits.view(B, 1, -1), past_key_values=past_key_values)
-        if inputs_embeds is None:
-            inputs_embeds = self._prompt_embeds(input_ids, input_features, input_features_mask)
-        else:
-            inputs_embeds = inputs_embeds.to(dev, bf16).clone()
-        B, S, _ = inputs_embeds.shape
-        kv_start = self._left_pad_starts(attention_mask, B, S, dev)
-        cache = past_key_values if past_key_values is not None else lm.new_cache(B, max(S, 1) + (kwargs.get("reserve_tokens", 0)))
-        logits = lm.prefill(inputs_embeds, kv_start, cache, logits_to_keep=logits_to_keep)
-        return CausalLMOutputWithPast(logits=logits, past_key_values=cache if (use_cache or past_key_values is not None) else None)
+        cache = past_key_values
+        try:
+            if cache is not None and cache.length > 0:
+                single = inputs_embeds is None and input_features is None and input_ids.shape[1] == 1
+                if single:
+                    B = input_ids.shape[0]
+                    if B != cache.B:
+                        raise AF3Error(f"KV cache was allocated for {cache.B} sequences, got {B}")
+                    cache.ensure_capacity(cache.length + 1)
+                    x, _ = ops.embed_scatter(input_ids.to(dev).reshape(-1).contiguous(), lm.model.embed_tokens.weight, -1, None, 0, 1, None)
+                    scratch = ops.decode_attention_scratch(B, lm.H, lm.D, cache.Tmax, dev)
+                    logits = lm.decode_step(x, cache, scratch)
+                    cache.length += 1
+                    return CausalLMOutputWithPast(logits=logits.view(B, 1, -1), past_key_values=cache)
+                # continuation chunk
+                if inputs_embeds is None:
+                    inputs_embeds = self._prompt_embeds(input_ids, input_features, input_features_mask)
+                else:
+                    inputs_embeds = inputs_embeds.to(dev, bf16).clone()
+                B, S, _ = inputs_embeds.shape
+                if attention_mask is not None:
+                    am = attention_mask[:, -S:] if attention_mask.shape[1] == cache.length + S else attention_mask
+                    if tuple(am.shape) != (B, S):
+                        raise AF3Error(f"attention_mask must cover the new chunk [B, {S}] or the full sequence [B, {cache.length + S}]")
+                    bad = (am == 0).any()
+                    msg = "a continuation chunk on a live cache must be unpadded (attention_mask all ones over the chunk)"
+                    if am.is_cuda:
+                        self._defer_check(bad, AF3Error, msg)
+                    elif bool(bad):
+                        raise AF3Error(msg)
+                cache.ensure_capacity(cache.length + S + (reserve_tokens or 0))
+                logits = lm.prefill(inputs_embeds, None, cache, logits_to_keep=logits_to_keep)
+                return CausalLMOutputWithPast(logits=logits, past_key_values=cache)
+            if inputs_embeds is None:
+                inputs_embeds = self._prompt_embeds(input_ids, input_features, input_features_mask)
+            else:
+                inputs_embeds = inputs_embeds.to(dev, bf16).clone()
+            B, S, _ = inputs_embeds.shape
+            kv_start = self._left_pad_starts(attention_mask, B, S, dev)
+            keep = bool(use_cache) or cache is not None
+            if cache is None:
+                # without use_cache the cache only lives for this call: exactly the prompt.  With it, room for a cached
+                # continuation is reserved (ADVICE r01: a zero reserve made the first decode step write past the allocation)
+                rows = S + (reserve_tokens if reserve_tokens is not None else 1) if keep else S
+                cache = lm.new_cache(B, AF3KVCache.bucket(rows) if keep else max(S, 1))
+            else:
+                cache.ensure_capacity(S + (reserve_tokens or 0))
+            logits = lm.prefill(inputs_embeds, kv_start, cache, logits_to_keep=logits_to_keep)
+            return CausalLMOutputWithPast(logits=logits, past_key_values=cache if keep else None)
+        finally:
+            self._raise_deferred()
 
     __call__ = forward  # nn.Module.__call__ hooks are not needed on the inference path
 
     # ---- greedy generation ([O] GEN:2131 generate -> GEN:2658 _sample with do_sample=False)
+    _IGNORED_WHEN_GREEDY = ("temperature", "top_p", "top_k", "min_p", "typical_p")        # unused by the reference too when do_sample=False
+    _ACCEPTED_DEFAULTS = {"num_beams": 1, "num_return_sequences": 1, "repetition_penalty": 1.0, "no_repeat_ngram_size": 0,
+                          "length_penalty": 1.0, "use_cache": True, "return_dict_in_generate": False, "output_scores": False,
+                          "output_logits": False, "num_beam_groups": 1, "penalty_alpha": None, "min_new_tokens": None,
+                          "min_length": 0, "assistant_model": None, "streamer": None, "logits_processor": None,
+                          "stopping_criteria": None, "bad_words_ids": None, "suppress_tokens": None, "synced_gpus": None}
+
+    def _generation_default(self, name):
+        gc = getattr(self, "generation_config", None)
+        return getattr(gc, name, None) if gc is not None else None
+
+    @_on_model_device
     @torch.no_grad()
     def generate(self, input_ids=None, attention_mask=None, input_features=None, input_features_mask=None,
-                 max_new_tokens=20, do_sample=False, eos_token_id=None, pad_token_id=None, use_cuda_graph=True,
-                 return_logits=False, **kwargs):
+                 max_new_tokens=None, max_length=None, do_sample=None, eos_token_id=None, pad_token_id=None, use_cuda_graph=True,
+                 return_logits=False, prefill_chunk_size=None, generation_config=None, **kwargs):
+        """Greedy decoding with the reference's `generate` call surface (prompt included in the returned ids, AF3M:547-551).
+        Defaults follow the reference: eos_token_id / pad_token_id / max_new_tokens / do_sample come from `generation_config`
+        (argument, else `self.generation_config`) when not passed; finished rows are padded and the loop stops once every row
+        has produced EOS (GEN:2797-2805).  Options of the reference this path does not implement raise instead of being ignored."""
+        if generation_config is not None:
+            saved, self.generation_config = getattr(self, "generation_config", None), generation_config
+            try:
+                return self.generate(input_ids=input_ids, attention_mask=attention_mask, input_features=input_features,
+                                     input_features_mask=input_features_mask, max_new_tokens=max_new_tokens, max_length=max_length,
+                                     do_sample=do_sample, eos_token_id=eos_token_id, pad_token_id=pad_token_id,
+                                     use_cuda_graph=use_cuda_graph, return_logits=return_logits, prefill_chunk_size=prefill_chunk_size, **kwargs)
+            finally:
+                self.generation_config = saved
+        for k, v in kwargs.items():
+            if k in self._IGNORED_WHEN_GREEDY:
+                continue
+            if k in self._ACCEPTED_DEFAULTS and (v == self._ACCEPTED_DEFAULTS[k] or v is None):
+                continue
+            raise AF3Error(f"generate(): option {k}={v!r} is not implemented on the B200 greedy path "
+                           "(greedy decoding, one sequence per prompt, no logits processors)")
+        if do_sample is None:
+            do_sample = bool(self._generation_default("do_sample"))
         if do_sample:
             raise AF3Error("only greedy decoding (do_sample=False) is implemented")
+        if input_ids is None:
+            raise AF3Error("generate() needs input_ids")
         lm = self.language_model
         lm._check_ready()
         dev = lm.lm_head.weight.device
         B, S = input_ids.shape
-        self._mark("start")
-        x = self._prompt_embeds(input_ids, input_features, input_features_mask)
-        self._mark("audio_done")
-        kv_start = self._left_pad_starts(attention_mask, B, S, dev)
-        use_graph = bool(use_cuda_graph and max_new_tokens > 2)
-        # Cache capacity is rounded up to a multiple of 256 rows: the captured graph depends on the capacity (cache pitch in the
-        # tensor maps, scratch sizes) but not on the prompt length, so prompts of different lengths that fall into the same
-        # bucket reuse one cache + graph.  The kernels only ever touch the live rows, the extra capacity costs memory only.
-        Tmax = -(-(S + max_new_tokens) // 256) * 256
-        # the captured graph holds raw addresses: key it on the weight storages too, so a re-pack (load_reference_state_dict) or
-        # a move (.to()) can never leave a stale graph replaying against freed memory
-        key = (B, Tmax, use_graph, os.environ.get("AF3_PDL", "1") != "0", str(dev),
-               lm.lm_head.weight.data_ptr(), lm._packed[0][0].data_ptr(), lm._packed[-1][2].data_ptr())
-        st = self._decode_state
-        if st is not None and st["key"] == key:
-            cache, step_fn = st["cache"], st["step"]       # same buffers -> the captured graph is valid as it stands
-            cache.reset()
-        else:
-            self._decode_state = st = None                 # free the previous shape's cache and graph first
-            cache = lm.new_cache(B, Tmax)
-            step_fn = self._decode_runner(B, cache, use_graph)
-            self._decode_state = {"key": key, "cache": cache, "step": step_fn}
-        logits = lm.prefill(x, kv_start, cache, logits_to_keep=1).view(B, -1)           # GEN:3724 _prefill
-        self._mark("prefill_done")
-        out = torch.empty((B, S + max_new_tokens), device=dev, dtype=torch.int64)
-        out[:, :S] = input_ids.to(dev)
-        eos = None
-        if eos_token_id is not None:
-            eos = torch.as_tensor([eos_token_id] if isinstance(eos_token_id, int) else list(eos_token_id), device=dev)
-            if pad_token_id is None:
-                pad_token_id = int(eos[0])
-            unfinished = torch.ones((B,), device=dev, dtype=torch.int64)
-        kept_logits = [logits.clone()] if return_logits else None
-        next_ids = ops.argmax(logits)                                                   # GEN:2793
-        result = self._token_loop(step_fn, cache, out, next_ids, logits, kept_logits, eos, unfinished if eos is not None else None,
-                                  pad_token_id, S, max_new_tokens)
-        self._mark("decode_done")
-        if return_logits:
-            return result, torch.stack(kept_logits, 1)
-        return result
+        if max_new_tokens is None:
+            max_new_tokens = self._generation_default("max_new_tokens")
+        if max_new_tokens is None:
+            ml = max_length if max_length is not None else (self._generation_default("max_length") or 20)
+            max_new_tokens = ml - S                                                      # GEN: max_length counts the prompt
+        if max_new_tokens < 1:
+            raise ValueError(f"max_new_tokens must be >= 1 (prompt length {S})")
+        if eos_token_id is None:
+            eos_token_id = self._generation_default("eos_token_id")
+        if pad_token_id is None:
+            pad_token_id = self._generation_default("pad_token_id")
+        if prefill_chunk_size is None:
+            prefill_chunk_size = self._generation_default("prefill_chunk_size")
+        try:
+            self._mark("start")
+            x = self._prompt_embeds(input_ids, input_features, input_features_mask)
+            self._mark("audio_done")
+            kv_start = self._left_pad_starts(attention_mask, B, S, dev)
+            use_graph = bool(use_cuda_graph and max_new_tokens > 2)
+            # Cache capacity is rounded up to a multiple of 256 rows: the captured graph depends on the capacity (cache pitch in the
+            # tensor maps, scratch sizes) but not on the prompt length, so prompts of different lengths that fall into the same
+            # bucket reuse one cache + graph.  The kernels only ever touch the live rows, the extra capacity costs memory only.
+            Tmax = AF3KVCache.bucket(S + max_new_tokens)
+            # the captured graph holds raw addresses: key it on the weight storages too, so a re-pack (load_reference_state_dict) or
+            # a move (.to()) can never leave a stale graph replaying against freed memory
+            key = (B, Tmax, use_graph, os.environ.get("AF3_PDL", "1") != "0", str(dev),
+                   lm.lm_head.weight.data_ptr(), lm._packed[0][0].data_ptr(), lm._packed[-1][2].data_ptr())
+            st = self._decode_state
+            if st is not None and st["key"] == key:
+                cache, step_fn = st["cache"], st["step"]       # same buffers -> the captured graph is valid as it stands
+                cache.reset()
+            else:
+                self._decode_state = st = None                 # free the previous shape's cache and graph first
+                cache = lm.new_cache(B, Tmax)
+                step_fn = self._decode_runner(B, cache, use_graph)
+                self._decode_state = {"key": key, "cache": cache, "step": step_fn}
+            if prefill_chunk_size is not None and 0 < prefill_chunk_size < S:
+                # chunked prefill (GEN:3770-3806): the prompt embeddings (audio rows already scattered in) go through the decoder in
+                # slices of prefill_chunk_size positions appended to the live cache; peak activation memory scales with the chunk
+                logits = None
+                for c0 in range(0, S, prefill_chunk_size):
+                    c1 = min(S, c0 + prefill_chunk_size)
+                    logits = lm.prefill(x[:, c0:c1].contiguous(), kv_start, cache, logits_to_keep=1 if c1 == S else -1)
+                logits = logits.view(B, -1)
+            else:
+                logits = lm.prefill(x, kv_start, cache, logits_to_keep=1).view(B, -1)           # GEN:3724 _prefill
+            self._mark("prefill_done")
+            out = torch.empty((B, S + max_new_tokens), device=dev, dtype=torch.int64)
+            out[:, :S] = input_ids.to(dev)
+            eos = unfinished = None
+            if eos_token_id is not None:
+                eos = torch.as_tensor([eos_token_id] if isinstance(eos_token_id, int) else list(eos_token_id), device=dev)
+                if pad_token_id is None:
+                    pad_token_id = int(eos[0])                                                # GEN: "Setting pad_token_id to eos_token_id"
+                unfinished = torch.ones((B,), device=dev, dtype=torch.int64)
+            kept_logits = [logits.clone()] if return_logits else None
+            next_ids = ops.argmax(logits)                                                   # GEN:2793
+            result = self._token_loop(step_fn, cache, out, next_ids, logits, kept_logits, eos, unfinished, pad_token_id, S, max_new_tokens)
+            self._mark("decode_done")
+            if return_logits:
+                return result, torch.stack(kept_logits, 1)
+            return result
+        finally:
+            self._raise_deferred()
 
     def release_decode_state(self):
         """Frees the KV cache and decode graph kept from the last generate() call."""
         self._decode_state = None
 
+    EOS_CHECK_EVERY = 8  # tokens between host reads of the "every row finished" flag (the reference syncs every token)
+
     def _token_loop(self, step_fn, cache, out, next_ids, logits, kept_logits, eos, unfinished, pad_token_id, S, max_new_tokens):
         return_logits = kept_logits is not None
         n_done = max_new_tokens
+        all_done = []  # per generated token: 0-dim device bool "every row has finished" (read in batches, not per token)
         for i in range(max_new_tokens):
             if eos is not None:
                 next_ids = next_ids * unfinished + pad_token_id * (1 - unfinished)      # GEN:2797
             out[:, S + i] = next_ids
             if eos is not None:
-                unfinished = unfinished & ~torch.isin(next_ids, eos)
-                if int(unfinished.max()) == 0:                                          # GEN:2805 (one sync per step)
-                    n_done = i + 1
-                    break
+                unfinished = unfinished & ~torch.isin(next_ids, eos)                    # GEN:2803 (EosTokenCriteria)
+                all_done.append(unfinished.max() == 0)
+                if (i + 1) % self.EOS_CHECK_EVERY == 0 or i + 1 == max_new_tokens:
+                    flags = torch.stack(all_done).cpu()                                 # GEN:2805, one sync per EOS_CHECK_EVERY tokens
+                    if bool(flags.any()):
+                        # tokens enqueued after the stopping step are pads of rows that had all finished: cut them off, the
+                        # result equals the reference's, which stops at exactly that step
+                        n_done = int(flags.nonzero()[0]) + 1
+                        break
             if i + 1 == max_new_tokens:
                 break
             logits, next_ids = step_fn(next_ids)   # one cached step incl. the greedy argmax (GEN:2793)
@@ -596,6 +781,8 @@ class AudioFlamingo3ForConditionalGeneration(nn.Module):
                 self.stage_host_t.append(("tok", time.perf_counter()))
             if return_logits:
                 kept_logits.append(logits.clone())
+        if return_logits:
+            del kept_logits[n_done:]
         return out[:, : S + n_done]
 
     def _decode_runner(self, B, cache, use_graph):
@@ -613,11 +800,13 @@ class AudioFlamingo3ForConditionalGeneration(nn.Module):
             # programmatic dependent launch along the whole step: each kernel's prologue and the GEMMs' weight
             # prefetch overlap the tail of the kernel before it (the kernels order their dependent accesses themselves)
             _lib.load().af3_set_pdl(1 if use_pdl else 0)
+            phase, ops.PHASE = ops.PHASE, "decode"
             try:
                 x, _ = ops.embed_scatter(next_ids, table, -1, None, 0, 1, None)
                 logits = lm.decode_step(x, cache, scratch)
                 return logits, ops.argmax(logits)
             finally:
+                ops.PHASE = phase
                 _lib.load().af3_set_pdl(0)
 
         if not use_graph:
@@ -634,8 +823,11 @@ class AudioFlamingo3ForConditionalGeneration(nn.Module):
                 torch.cuda.synchronize()
                 prof, ops.PROFILE = ops.PROFILE, None  # timing events cannot be recorded inside a capture
                 n0 = ops.LAUNCHES
+                t0 = len(ops.TRACE_LOG) if ops.TRACE_LOG is not None else 0
                 with torch.cuda.graph(g):
                     state["out"] = eager(ids_buf)
+                if ops.TRACE_LOG is not None:  # timeline tool: which trace-log entries are the captured step's launches
+                    ops.TRACE_LOG.append(("graph_capture", t0, len(ops.TRACE_LOG)))
                 state["launches"] = ops.LAUNCHES - n0
                 ops.LAUNCHES = n0  # capture launched nothing; replays are counted below
                 ops.PROFILE = prof
@@ -667,20 +859,33 @@ class MusicFlamingoForConditionalGeneration(AudioFlamingo3ForConditionalGenerati
         self._mf_frame_step = config.audio_frame_step
 
     def _build_audio_timestamps(self, input_ids, post_lengths, max_post_length):
-        """Seconds of every encoder output row; index arithmetic of [O] modular_musicflamingo.py:250-285 on the device."""
-        audio_token_mask = input_ids == self.config.audio_token_id
-        diff = torch.diff(torch.nn.functional.pad(audio_token_mask.int(), (1, 1), value=0), dim=1)
-        _, starts = torch.where(diff == 1)
-        _, ends = torch.where(diff == -1)
-        sample_lengths = (ends - starts).to(torch.long)
+        """Start time (in seconds) of every pooled encoder frame, fp32 [W, max_post_length]: what the reference derives in
+        [O] modular_musicflamingo.py:250-285.  A clip longer than 30 s is several consecutive windows feeding ONE run of <sound>
+        placeholders; frame t of the k-th window of its clip starts at (k * max_post_length + t) * 4 * frame_step.
+        Own formulation, sync-free (no torch.where / boolean indexing): every placeholder gets (its ordinal among all placeholders,
+        the index of the run it belongs to); a window's run is looked up at the ordinal of its first frame, and k is the window
+        index minus the first window index of that run."""
+        dev = post_lengths.device
+        is_audio = (input_ids == self.config.audio_token_id)                                  # [B, S]
+        left_is_audio = torch.zeros_like(is_audio)
+        left_is_audio[:, 1:] = is_audio[:, :-1]                                               # runs never continue across rows
+        flat = is_audio.reshape(-1)
+        n_pos = flat.numel()
+        run_of_pos = torch.cumsum((is_audio & ~left_is_audio).reshape(-1).to(torch.long), 0) - 1
+        ordinal_of_pos = torch.cumsum(flat.to(torch.long), 0) - 1
+        # run index by placeholder ordinal; non-placeholder positions write into the spare last slot
+        run_of_ordinal = torch.zeros((n_pos + 1,), device=dev, dtype=torch.long)
+        run_of_ordinal.scatter_(0, torch.where(flat, ordinal_of_pos, torch.full_like(ordinal_of_pos, n_pos)), run_of_pos)
+        W = post_lengths.shape[0]
+        first_ordinal = torch.cumsum(post_lengths.to(torch.long), 0) - post_lengths.to(torch.long)
+        run_of_window = run_of_ordinal[first_ordinal.clamp(max=n_pos - 1)]
+        widx = torch.arange(W, device=dev, dtype=torch.long)
+        first_window_of_run = torch.full((n_pos + 1,), W, device=dev, dtype=torch.long)
+        first_window_of_run.scatter_reduce_(0, run_of_window, widx, reduce="amin", include_self=True)
+        k = (widx - first_window_of_run[run_of_window]).to(torch.float32)
         step = self._mf_frame_step * 4
-        frame_offsets = torch.arange(max_post_length, device=post_lengths.device, dtype=torch.float32) * step
-        cumsum_post = torch.cat([torch.zeros(1, device=post_lengths.device), torch.cumsum(post_lengths, dim=0)[:-1]])
-        cumsum_samples = torch.cumsum(sample_lengths, dim=0)
-        sample_indices = torch.searchsorted(cumsum_samples, cumsum_post, right=True)
-        sample_start_rows = torch.searchsorted(sample_indices, torch.arange(sample_lengths.shape[0], device=post_lengths.device))
-        window_indices = torch.arange(post_lengths.shape[0], device=post_lengths.device) - sample_start_rows[sample_indices]
-        return window_indices.unsqueeze(1) * max_post_length * step + frame_offsets
+        frame_t = torch.arange(max_post_length, device=dev, dtype=torch.float32) * step
+        return k.unsqueeze(1) * max_post_length * step + frame_t
 
     def _post_encoder(self, enc, W, Tp, input_features_mask, input_ids):
         if input_ids is None:

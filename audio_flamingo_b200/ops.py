@@ -18,6 +18,8 @@ bf16 = torch.bfloat16
 # ---- instrumentation used by bench.py (counts are claims about OUR kernels; see DESIGN.md "measurement")
 LAUNCHES = 0      # CUDA kernels launched through the C ABI since the last reset (graph replays add their captured count)
 PROFILE = None    # when a dict: (kind, n_tok, n_feat, K, flags) -> list of (cuda start event, end event)
+PHASE = None      # tag added to PROFILE keys ("decode" inside the cached decode step): bench.py weights those by the graph replays
+TRACE_LOG = None  # when a list (af3_trace_begin open): (key, first slot, slot after the last) per C-ABI call, in launch order
 
 
 def _count(n: int) -> None:
@@ -29,9 +31,12 @@ class _Timed:
     """Brackets one C-ABI call with CUDA events on the current stream when PROFILE is enabled."""
 
     def __init__(self, key):
-        self.key = key if PROFILE is not None else None
+        self.key = key + (PHASE,) if PROFILE is not None else None
+        self.tkey = key if TRACE_LOG is not None else None
 
     def __enter__(self):
+        if self.tkey is not None:
+            self.seq0 = _lib.load().af3_trace_seq()
         if self.key is not None:
             self.e0 = torch.cuda.Event(enable_timing=True)
             self.e1 = torch.cuda.Event(enable_timing=True)
@@ -39,6 +44,8 @@ class _Timed:
         return self
 
     def __exit__(self, *exc):
+        if self.tkey is not None:
+            TRACE_LOG.append((self.tkey, self.seq0, _lib.load().af3_trace_seq()))
         if self.key is not None:
             self.e1.record()
             PROFILE.setdefault(self.key, []).append((self.e0, self.e1))
@@ -52,6 +59,10 @@ def _req(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
         raise _lib.AF3Error(f"{name} must be {dtype}, got {t.dtype}")
     if not t.is_contiguous():
         raise _lib.AF3Error(f"{name} must be contiguous")
+    if t.device.index != torch.cuda.current_device():
+        # the C ABI launches on the current device (include/af3b200.h); launching cuda:0 kernels on cuda:1 pointers would fault
+        raise _lib.AF3Error(f"{name} lives on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}: "
+                            "wrap the call in `with torch.cuda.device(...)` (the model's forward/generate do)")
     return t
 
 

@@ -20,6 +20,30 @@ HOP = 160
 MAX_AUDIO_LEN_S = 600
 
 
+def slaney_mel_filterbank(n_mels: int = 128, n_freq_bins: int = 201, f_max: float = 8000.0) -> np.ndarray:
+    """[n_freq_bins, n_mels] float64 triangular mel filterbank of the Whisper front end (a2 of SURVEY.md 8-a): Slaney's
+    auditory-toolbox mel scale (linear 200/3 Hz per mel below 1 kHz, 27 mels per factor 6.4 above), triangles drawn in Hz over
+    the rFFT bin centres 0..f_max, each scaled by 2 / (its bandwidth) ("slaney" area normalisation).
+    Own construction (one filter at a time); tests/test_host_logic_cpu.py asserts it is BIT-identical to the table the
+    reference builds with transformers.audio_utils.mel_filter_bank(201, 128, 0, 8000, 16000, "slaney", "slaney")
+    ([O] WFE:95-103 -> AU:453-544), so the product no longer imports the reference package for a constant."""
+    knee_hz, knee_mel = 1000.0, 15.0
+    mels_per_ln = 27.0 / np.log(6.4)
+    top_mel = knee_mel + np.log(f_max / knee_hz) * mels_per_ln if f_max >= knee_hz else 3.0 * f_max / 200.0
+    mel_pts = np.linspace(0.0, top_mel, n_mels + 2)
+    edges_hz = 200.0 * mel_pts / 3.0
+    upper = mel_pts >= knee_mel
+    edges_hz[upper] = knee_hz * np.exp((np.log(6.4) / 27.0) * (mel_pts[upper] - knee_mel))
+    bin_hz = np.linspace(0, f_max, n_freq_bins)
+    bank = np.zeros((n_freq_bins, n_mels), dtype=np.float64)
+    for m in range(n_mels):
+        lo, mid, hi = edges_hz[m], edges_hz[m + 1], edges_hz[m + 2]
+        rising = (bin_hz - lo) / (mid - lo)
+        falling = (hi - bin_hz) / (hi - mid)
+        bank[:, m] = np.maximum(0.0, np.minimum(rising, falling)) * (2.0 / (hi - lo))
+    return bank
+
+
 def split_windows(audio: list[np.ndarray], max_audio_len: int = MAX_AUDIO_LEN_S):
     """[O] AF3P:159-179.  Returns (flat_chunks, per_sample_windows)."""
     max_windows = int(max_audio_len // CHUNK_LENGTH)
@@ -99,20 +123,23 @@ class AF3FeatureExtractor:
     def __init__(self, device="cuda", feature_size=128):
         if feature_size != 128:
             raise AF3Error("AF3 uses 128 mel bins")
-        from transformers.audio_utils import mel_filter_bank  # the reference's own constant generator (AU:453-544)
-
-        self.mel_filters = mel_filter_bank(num_frequency_bins=201, num_mel_filters=128, min_frequency=0.0, max_frequency=8000.0,
-                                           sampling_rate=SAMPLING_RATE, norm="slaney", mel_scale="slaney")
+        self.mel_filters = slaney_mel_filterbank(128, 201, SAMPLING_RATE / 2)
         self.device = torch.device(device)
         self.tables = ops.LogMelTables(self.mel_filters, self.device)
         self.n_samples = WINDOW_SAMPLES
         self.nb_max_frames = WINDOW_SAMPLES // HOP
         self.sampling_rate = SAMPLING_RATE
         self._pinned = None
+        self._pinned_busy = None  # CUDA event recorded after the last async H2D copy out of the staging buffer
 
     def _stage(self, chunks: list[np.ndarray]):
         """Zero-padded [n, 480000] fp32 in pinned host memory + per-clip sample counts."""
         n = len(chunks)
+        if self._pinned_busy is not None:
+            # the previous call's non-blocking copy may still be reading the staging buffer: rewriting it now would corrupt
+            # that batch's waveforms (ADVICE r01).  Waits only for that one copy, not for the stream.
+            self._pinned_busy.synchronize()
+            self._pinned_busy = None
         if self._pinned is None or self._pinned.shape[0] < n:
             self._pinned = torch.empty((n, self.n_samples), dtype=torch.float32).pin_memory()
         buf = self._pinned[:n]
@@ -130,7 +157,10 @@ class AF3FeatureExtractor:
         if isinstance(raw_speech, np.ndarray) and raw_speech.ndim == 1:
             raw_speech = [raw_speech]
         host, lens = self._stage(list(raw_speech))
-        wave = host.to(self.device, non_blocking=True)
+        with torch.cuda.device(self.device):
+            wave = host.to(self.device, non_blocking=True)
+            self._pinned_busy = torch.cuda.Event()
+            self._pinned_busy.record()
         return self.from_device_waveform(wave, lens)
 
     def from_device_waveform(self, wave: torch.Tensor, n_valid_samples):

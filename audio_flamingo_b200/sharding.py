@@ -38,10 +38,15 @@ def shard_rows(n_rows: int, world_size: int, rank: int, weights: list[int] | Non
     return cuts[rank], cuts[rank + 1]
 
 
-def gather_tokens(local_tokens: torch.Tensor, counts: list[int] | None = None, group=None) -> torch.Tensor:
-    """All-gather generated ids [B_local, L] -> [sum B_local, L] on every rank (rows in rank order).
+def gather_tokens(local_tokens: torch.Tensor, counts: list[int] | None = None, group=None, pad_token_id: int = 0,
+                  assume_equal_length: bool = False) -> torch.Tensor:
+    """All-gather generated ids [B_local, L_local] -> [sum B_local, max L] on every rank (rows in rank order).
 
     counts: rows per rank (needed only when they differ; shorter shards are padded for the collective and trimmed).
+    Ranks may hold different L: generate() returns fewer columns on a rank whose rows all hit EOS early, and prompts are left
+    padded per shard.  The column counts are exchanged first (one tiny all-gather), every shard is right-padded with
+    `pad_token_id` to the longest one for the id all-gather, so the collective always sees equal shapes
+    (assume_equal_length=True skips the exchange when the caller knows every rank returns the same L).
     Without an initialised process group (single GPU) this is the identity.
     """
     import torch.distributed as dist
@@ -54,11 +59,18 @@ def gather_tokens(local_tokens: torch.Tensor, counts: list[int] | None = None, g
     if counts is None:
         counts = [local_tokens.shape[0]] * world
     mx = max(counts)
+    dev = local_tokens.device
+    if assume_equal_length:  # caller guarantees it (no EOS, same prompt length everywhere): skips the length exchange and its host sync
+        L = local_tokens.shape[1]
+    else:
+        lens = torch.empty((world,), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(lens, torch.tensor([local_tokens.shape[1]], dtype=torch.int64, device=dev), group=group)
+        L = int(lens.max())
     buf = local_tokens
-    if local_tokens.shape[0] < mx:
-        pad = torch.zeros((mx - local_tokens.shape[0], local_tokens.shape[1]), dtype=local_tokens.dtype, device=local_tokens.device)
-        buf = torch.cat([local_tokens, pad], 0)
-    out = torch.empty((world * mx, local_tokens.shape[1]), dtype=local_tokens.dtype, device=local_tokens.device)
+    if buf.shape[0] < mx or buf.shape[1] < L:
+        buf = torch.full((mx, L), pad_token_id, dtype=local_tokens.dtype, device=dev)
+        buf[: local_tokens.shape[0], : local_tokens.shape[1]] = local_tokens
+    out = torch.empty((world * mx, L), dtype=local_tokens.dtype, device=dev)
     dist.all_gather_into_tensor(out, buf.contiguous(), group=group)
     if all(c == mx for c in counts):
         return out

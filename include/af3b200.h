@@ -10,8 +10,14 @@
  * Conventions: plain pointers and sizes only (no torch types); every pointer is a DEVICE pointer unless the
  * parameter name starts with h_; `stream` is a cudaStream_t passed as void*; all calls are asynchronous on
  * `stream`; return 0 on success, non-zero on error with a message available from af3_last_error() (thread
- * local).  No ownership transfer: outputs are written into caller-allocated buffers.  Not re-entrant per
- * engine handle; one handle per GPU.  bf16 tensors are row-major with the stated pitch.
+ * local).  No ownership transfer: outputs are written into caller-allocated buffers.  bf16 tensors are row-major with
+ * the stated pitch.
+ * State and threading (there is NO engine handle): every call launches on the CALLER'S CURRENT CUDA device, which must
+ * be the device that owns all pointers of the call (cudaSetDevice first; per-device kernel attributes and SM counts
+ * are cached per device ordinal, so several GPUs in one process work).  The process-wide switches af3_set_pdl and
+ * af3_trace_begin/end are plain globals: drive the library from one launching thread per process (the reference's
+ * host is single-threaded too).  Workspaces are caller-owned and must not be shared by concurrent
+ * streams.
  */
 #ifndef AF3B200_H
 #define AF3B200_H
@@ -27,6 +33,18 @@ int af3_abi_version(void);
  * attention, embedding gather, argmax): the next kernel's prologue and weight prefetch overlap the previous kernel's
  * tail; results are identical.  Process-wide switch, off by default. */
 void af3_set_pdl(int enable);
+
+/* In-graph timeline of the decode-step kernel chain (measurement aid; no reference counterpart).  Between
+ * af3_trace_begin(buf, bytes) and af3_trace_end() every launch of a decode-step kernel (few-token GEMM, RMSNorm, rope
+ * table, decode attention, embedding gather, argmax) is given the next slot of af3_trace_slot_bytes() bytes in `buf`
+ * (device memory, zero-initialised by the caller) and its first 160 CTAs store %globaltimer there at 4 marks: entry,
+ * after griddepcontrol.wait, main loop done, exit.  The slot address is a launch parameter, so a CUDA graph captured
+ * while the trace is open keeps recording on every replay (the buffer holds the last replay).  af3_trace_seq() = slots
+ * handed out so far; af3_trace_end() returns that count and stops handing out slots.  Process-wide, not thread-safe. */
+size_t af3_trace_slot_bytes(void);
+int af3_trace_begin(void* buf, size_t bytes);
+int af3_trace_end(void);
+int af3_trace_seq(void);
 
 /* ---- epilogue flags for af3_gemm_bf16 ---- */
 #define AF3_EPI_BIAS 1
@@ -107,7 +125,7 @@ int af3_rotary_time_emb(void* stream, void* x, const float* timestamps, const fl
 /* Decode-step fusion of the q/k/v projection with RoPE and the KV append (Q2M:199-215 + CACHE:119-120 in one kernel):
  * out rows get the ROTATED query heads (columns [0, H*D)); rotated keys and the values go straight into the caches at
  * slot *pos_dev.  rope_cs [n_tok][D/2][2] fp32 from af3_rope_table (once per step, shared by all layers).
- * n_tok <= 32, D = 128, bias required (Qwen2 q/k/v have biases). */
+ * n_tok <= 64, D = 128, bias required (Qwen2 q/k/v have biases). */
 int af3_rope_table(void* stream, float* rope_cs, int B, int D, const int* pos_dev, const int* kv_start,
                    const float* inv_freq);
 int af3_gemm_qkv_rope(void* stream, const void* x, int ldx, const void* w, int ldw, const void* bias, void* q_out, int ldo,

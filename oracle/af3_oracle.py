@@ -93,6 +93,21 @@ def hf_model(preset: str | dict, seed: int = 0, dtype=torch.float32, device="cpu
     return model
 
 
+def hf_restore_fp32_rotary(model):
+    """Recompute the rotary inv_freq buffers in fp32 on the CPU and move them to the model's device.  The reference's normal
+    loading path (from_pretrained(dtype=torch.bfloat16)) casts PARAMETERS; this non-persistent buffer is built in fp32
+    ([O] Q2M:86-89) and stays fp32.  A blanket model.to(torch.bfloat16) -- convenient in tests -- would round it to 8 bits and
+    run RoPE at slightly different frequencies than any real deployment of the reference; call this after such a cast (and after
+    to_empty(), which leaves the buffer uninitialised)."""
+    for mod in model.modules():
+        if hasattr(mod, "inv_freq") and hasattr(mod, "compute_default_rope_parameters"):
+            inv, _ = mod.compute_default_rope_parameters(mod.config)
+            dev = mod.inv_freq.device if mod.inv_freq.device.type != "meta" else "cpu"
+            mod.inv_freq = inv.to(dev)
+            mod.original_inv_freq = inv.clone().to(dev)
+    return model
+
+
 def hf_feature_extractor():
     from transformers import WhisperFeatureExtractor
 

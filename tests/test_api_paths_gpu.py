@@ -1,0 +1,258 @@
+"""API paths of the drop-in surface that round 1 left untested, each against the
+unmodified HF reference on the same GPU (bf16, same seeded synthetic weights):
+  * generate(eos_token_id=...) with rows finishing at different steps / every row finishing early   [O] GEN:2797-2805
+  * forward(use_cache=True) + cached single-token forward() steps, including cache growth           [O] AF3M:580-592, CACHE:119-120
+  * a second chat turn with NEW audio appended to a live cache (config 5 semantics)
+  * inputs_embeds, batch 1, more than 32 / 64 sequences per GPU, 4 <sound> spans + 512 text tokens x 16 sequences
+  * chunked prefill (GEN:3770-3806) == unchunked
+  * options of the reference that this path does not implement raise instead of being ignored
+Tolerance for logits: max |diff| <= 6 % of the reference logit std (bf16 GEMM chains; same bound as tests/test_model_gpu.py);
+token ids: exact."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+bf16 = torch.bfloat16
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import af3_oracle
+
+    return af3_oracle
+
+
+@pytest.fixture(scope="module")
+def tiny(O):
+    from audio_flamingo_b200 import AudioFlamingo3ForConditionalGeneration
+
+    ref32 = O.hf_model("tiny", seed=0, sharpen=8.0)
+    ours = AudioFlamingo3ForConditionalGeneration.from_reference(ref32, device="cuda")
+    ref16 = O.hf_restore_fp32_rotary(O.hf_model("tiny", seed=0, sharpen=8.0).to("cuda", bf16))
+    return ref32.config, ours, ref16
+
+
+def _audio_inputs(O, cfg, secs, seed=1):
+    waves = O.synth_waveforms(len(secs), secs, seed=seed)
+    feats, fmask = O.hf_features(waves)
+    toks = [O.post_pool_len(int(n)) for n in fmask.sum(-1)]
+    ids, am = O.synth_prompt(toks, cfg.text_config.vocab_size, cfg.audio_token_id, seed=seed + 1)
+    return feats, fmask, ids, am
+
+
+def _kw(feats, fmask, ids, am, ref=False):
+    f = feats.cuda().to(bf16) if ref else feats.cuda()
+    return dict(input_ids=ids.cuda(), attention_mask=am.cuda(), input_features=f, input_features_mask=fmask.cuda())
+
+
+def test_generate_eos_rows_finish_at_different_steps(O, tiny):
+    cfg, ours, ref16 = tiny
+    feats, fmask, ids, am = _audio_inputs(O, cfg, [10.0, 4.3, 30.0], seed=5)
+    S, new = ids.shape[1], 24
+    with torch.no_grad():
+        free = ref16.generate(**_kw(feats, fmask, ids, am, ref=True), max_new_tokens=new, do_sample=False)[:, S:].cpu()
+    assert torch.equal(ours.generate(**_kw(feats, fmask, ids, am), max_new_tokens=new)[:, S:].cpu(), free)
+    # (a) rows 0 / 1 finish at steps 2 / 9, row 2 keeps going unless it happens to emit one of the two ids: padded rows, full length
+    # (b) every row has an EOS id somewhere in its first 12 tokens: the loop stops early, the result is shorter than max_new_tokens
+    eos_a = [int(free[0, 2]), int(free[1, 9])]
+    eos_b = [int(free[0, 2]), int(free[1, 9]), int(free[2, 11])]
+    for eos in (eos_a, eos_b, eos_a[0]):
+        with torch.no_grad():
+            g_ref = ref16.generate(**_kw(feats, fmask, ids, am, ref=True), max_new_tokens=new, do_sample=False, eos_token_id=eos,
+                                   pad_token_id=0).cpu()
+        for graph in (True, False):
+            g = ours.generate(**_kw(feats, fmask, ids, am), max_new_tokens=new, eos_token_id=eos, pad_token_id=0, use_cuda_graph=graph).cpu()
+            assert g.shape == g_ref.shape, (eos, g.shape, g_ref.shape)
+            assert torch.equal(g, g_ref), (eos, g[:, S:], g_ref[:, S:])
+    assert g_ref.shape[1] <= S + new
+    # defaults come from the reference model's generation_config when present
+    saved = ours.generation_config
+    try:
+        from transformers import GenerationConfig
+
+        ours.generation_config = GenerationConfig(eos_token_id=eos_b, pad_token_id=0, max_new_tokens=new, do_sample=False)
+        with torch.no_grad():
+            g_ref = ref16.generate(**_kw(feats, fmask, ids, am, ref=True), generation_config=ours.generation_config).cpu()
+        assert torch.equal(ours.generate(**_kw(feats, fmask, ids, am)).cpu(), g_ref)
+    finally:
+        ours.generation_config = saved
+
+
+def test_generate_rejects_unimplemented_options(O, tiny):
+    from audio_flamingo_b200 import AF3Error
+
+    cfg, ours, _ = tiny
+    feats, fmask, ids, am = _audio_inputs(O, cfg, [3.0], seed=6)
+    for bad in (dict(num_beams=4), dict(repetition_penalty=1.2), dict(do_sample=True), dict(some_unknown_option=1)):
+        with pytest.raises(AF3Error):
+            ours.generate(**_kw(feats, fmask, ids, am), max_new_tokens=4, **bad)
+    # inert options of the reference are accepted
+    ours.generate(**_kw(feats, fmask, ids, am), max_new_tokens=3, num_beams=1, temperature=0.7, top_p=0.9, use_cache=True)
+
+
+def _logit_check(lo, lr, what):
+    lo, lr = lo.float().cpu(), lr.float().cpu()
+    err, std = (lo - lr).abs().max().item(), lr.std().item()
+    assert err <= 0.06 * std, f"{what}: max |diff| {err:.4f} vs logit std {std:.3f}"
+    top2 = lr.topk(2, dim=-1).values
+    safe = (top2[..., 0] - top2[..., 1]) > 2 * err
+    assert torch.equal(lo.argmax(-1)[safe], lr.argmax(-1)[safe]), what
+    return err
+
+
+@pytest.mark.parametrize("exact_capacity", [False, True])
+def test_cached_forward_continuation_matches_reference(O, tiny, exact_capacity):
+    """model(..., use_cache=True) then model(next_token, past_key_values=...) -- the manual loop users write -- vs the same loop on
+    the HF model with its DynamicCache.  exact_capacity: the prompt is prefilled into a cache with no free slot, so the first cached
+    step must grow it (round 1 wrote past the allocation here)."""
+    cfg, ours, ref16 = tiny
+    feats, fmask, ids, am = _audio_inputs(O, cfg, [10.0, 4.3], seed=7)
+    B, S = ids.shape
+    with torch.no_grad():
+        r = ref16(**_kw(feats, fmask, ids, am, ref=True), use_cache=True)
+    if exact_capacity:
+        cache = ours.language_model.new_cache(B, S)
+        o = ours(**_kw(feats, fmask, ids, am), past_key_values=cache)
+        assert o.past_key_values is cache and cache.Tmax == S
+    else:
+        o = ours(**_kw(feats, fmask, ids, am), use_cache=True)
+        assert o.past_key_values.Tmax >= S + 1
+    _logit_check(o.logits[am.bool()], r.logits[am.bool()], "prefill")
+    cache, hf_cache = o.past_key_values, r.past_key_values
+    mask = am.cuda()
+    tok = r.logits[:, -1].argmax(-1)
+    for step in range(6):
+        mask = torch.cat([mask, torch.ones((B, 1), dtype=mask.dtype, device="cuda")], 1)
+        with torch.no_grad():
+            r = ref16(input_ids=tok[:, None], attention_mask=mask, past_key_values=hf_cache, use_cache=True)
+        o = ours(input_ids=tok[:, None], attention_mask=mask, past_key_values=cache)
+        assert o.logits.shape == r.logits.shape == (B, 1, cfg.text_config.vocab_size)
+        assert cache.get_seq_length() == hf_cache.get_seq_length() == S + step + 1
+        _logit_check(o.logits, r.logits, f"cached step {step}")
+        tok = r.logits[:, -1].argmax(-1)   # teacher forcing with the reference's tokens
+    if exact_capacity:
+        assert cache.Tmax > S
+
+
+def test_second_turn_with_new_audio_on_live_cache(O, tiny):
+    """Chat turn 2 brings its own audio: its chunk (text + <sound> span + text) is appended to the cache of turn 1.  Checked against
+    the reference run ONCE over the concatenated conversation with both clips (causal attention => identical)."""
+    from audio_flamingo_b200.processing import expand_audio_spans
+
+    cfg, ours, ref16 = tiny
+    aid, V = cfg.audio_token_id, cfg.text_config.vocab_size
+    waves = O.synth_waveforms(2, [6.0, 3.5], seed=30)
+    feats, fmask = O.hf_features(waves)
+    n1, n2 = [O.post_pool_len(int(n)) for n in fmask.sum(-1)]
+    rs = np.random.RandomState(8)
+    t = lambda n: rs.randint(1, V - 2, size=n).tolist()  # noqa: E731
+    turn1 = torch.tensor([expand_audio_spans(t(4) + [aid] + t(9), aid, [n1])])
+    turn2 = torch.tensor([expand_audio_spans(t(6) + [aid] + t(5), aid, [n2])])
+    both = torch.cat([turn1, turn2], 1)
+    with torch.no_grad():
+        r = ref16(input_ids=both.cuda(), attention_mask=torch.ones_like(both).cuda(), input_features=feats.cuda().to(bf16),
+                  input_features_mask=fmask.cuda()).logits
+    o1 = ours(input_ids=turn1.cuda(), attention_mask=torch.ones_like(turn1).cuda(), input_features=feats[:1].cuda(),
+              input_features_mask=fmask[:1].cuda(), use_cache=True)
+    S1 = turn1.shape[1]
+    _logit_check(o1.logits, r[:, :S1], "turn 1")
+    # one decode step in between is NOT taken here: the reference conversation is the plain concatenation
+    o2 = ours(input_ids=turn2.cuda(), attention_mask=torch.ones_like(both).cuda(), input_features=feats[1:].cuda(),
+              input_features_mask=fmask[1:].cuda(), past_key_values=o1.past_key_values)
+    assert o2.past_key_values.get_seq_length() == both.shape[1]
+    _logit_check(o2.logits, r[:, S1:], "turn 2 on the live cache")
+    # a padded continuation chunk is refused (the kernels keep one contiguous live range per row)
+    from audio_flamingo_b200 import AF3Error
+
+    bad_mask = torch.ones_like(turn2)
+    bad_mask[0, 0] = 0
+    with pytest.raises(AF3Error):
+        ours(input_ids=turn2.cuda(), attention_mask=bad_mask, past_key_values=o2.past_key_values)
+
+
+def test_inputs_embeds_and_batch_one(O, tiny):
+    cfg, ours, ref16 = tiny
+    feats, fmask, ids, am = _audio_inputs(O, cfg, [7.0], seed=9)
+    with torch.no_grad():
+        emb = ref16.get_input_embeddings()(ids.cuda())
+        r = ref16(inputs_embeds=emb, attention_mask=am.cuda()).logits
+    o = ours(inputs_embeds=emb.clone(), attention_mask=am.cuda())
+    _logit_check(o.logits, r, "inputs_embeds")
+    with pytest.raises(ValueError):
+        ours(input_ids=ids.cuda(), inputs_embeds=emb)
+    with torch.no_grad():
+        g_ref = ref16.generate(**_kw(feats, fmask, ids, am, ref=True), max_new_tokens=10, do_sample=False)
+    assert torch.equal(ours.generate(**_kw(feats, fmask, ids, am), max_new_tokens=10), g_ref)
+
+
+@pytest.mark.parametrize("B", [40, 70])
+def test_more_than_32_sequences_per_gpu(O, tiny, B):
+    """VERDICT r01 missing #7: the decode step was limited to 32 sequences.  40 = two 32-token column tiles of the fused
+    few-token q/k/v GEMM; 70 = the token-major GEMM + stand-alone RoPE/append kernel."""
+    cfg, ours, ref16 = tiny
+    V = cfg.text_config.vocab_size
+    rs = np.random.RandomState(B)
+    lens = rs.randint(6, 30, size=B)
+    S = int(lens.max())
+    ids = torch.zeros((B, S), dtype=torch.int64)
+    am = torch.zeros((B, S), dtype=torch.int64)
+    for b, n in enumerate(lens):
+        ids[b, S - n:] = torch.from_numpy(rs.randint(1, V - 2, size=n))
+        am[b, S - n:] = 1
+    with torch.no_grad():
+        g_ref = ref16.generate(input_ids=ids.cuda(), attention_mask=am.cuda(), max_new_tokens=8, do_sample=False)
+    g = ours.generate(input_ids=ids.cuda(), attention_mask=am.cuda(), max_new_tokens=8)
+    g_eager = ours.generate(input_ids=ids.cuda(), attention_mask=am.cuda(), max_new_tokens=8, use_cuda_graph=False)
+    assert torch.equal(g, g_eager)
+    same = (g == g_ref).all(1)
+    assert int(same.sum()) >= B - 1, f"{int(same.sum())}/{B} rows identical"   # at most one bf16 near-tie among 8 x B decisions
+
+
+def test_config5_layout_four_audio_spans_512_text_tokens_batch16(O, tiny):
+    """BASELINE config 5 layout (AF3-Chat): 4 interleaved <sound> spans + 512 text tokens per sequence, 16 sequences (tiny
+    weights): 64 windows through the tower in one call, 4 spans per row scattered into the prompt."""
+    from audio_flamingo_b200 import AF3FeatureExtractor
+    from audio_flamingo_b200.processing import audio_token_length, expand_audio_spans, left_pad
+
+    cfg, ours, ref16 = tiny
+    aid, V = cfg.audio_token_id, cfg.text_config.vocab_size
+    B, spans = 16, 4
+    rs = np.random.RandomState(55)
+    secs = rs.uniform(1.0, 4.0, size=B * spans).round(2).tolist()
+    waves = O.synth_waveforms(B * spans, secs, seed=77)
+    fe = AF3FeatureExtractor("cuda")
+    fo = fe(waves, sampling_rate=16000)
+    frames = fo["attention_mask"].sum(-1).cpu().tolist()
+    counts = [int(audio_token_length(f)) for f in frames]
+    rows = []
+    for b in range(B):
+        txt = [rs.randint(1, V - 2, size=n).tolist() for n in (100, 100, 100, 100, 112)]   # 512 text tokens
+        row = txt[0] + [aid] + txt[1] + [aid] + txt[2] + [aid] + txt[3] + [aid] + txt[4]
+        rows.append(expand_audio_spans(row, aid, counts[b * spans:(b + 1) * spans]))
+    ids, am = left_pad(rows)
+    feats_ref, fmask_ref = O.hf_features(waves)
+    with torch.no_grad():
+        r = ref16(input_ids=ids.cuda(), attention_mask=am.cuda(), input_features=feats_ref.cuda().to(bf16),
+                  input_features_mask=fmask_ref.cuda(), logits_to_keep=1).logits
+    o = ours(input_ids=ids.cuda(), attention_mask=am.cuda(), input_features=fo["input_features"],
+             input_features_mask=fo["input_features_mask"], logits_to_keep=1).logits
+    assert o.shape == r.shape == (B, 1, V)
+    _logit_check(o, r, "config-5 layout")
+
+
+@pytest.mark.parametrize("chunk,exact", [(100, True), (128, False), (37, False)])
+def test_chunked_prefill_equals_unchunked(O, tiny, chunk, exact):
+    """[O] GEN:3770-3806 semantics: the prompt goes through the decoder in slices appended to the live cache.  Every query row sees
+    the same keys in the same tile order as in the one-pass prefill; with slices of more than 64 tokens every GEMM also runs the same
+    (token-major) kernel, so ids AND logits are bit-identical (chunk 100: 200 + 200 + 160 tokens).  A short last slice takes the
+    few-token split-K GEMM, whose fp32 summation order differs: ids identical, logits within bf16 noise."""
+    cfg, ours, _ = tiny
+    feats, fmask, ids, am = _audio_inputs(O, cfg, [10.0, 4.3], seed=12)
+    g0, l0 = ours.generate(**_kw(feats, fmask, ids, am), max_new_tokens=6, return_logits=True)
+    g1, l1 = ours.generate(**_kw(feats, fmask, ids, am), max_new_tokens=6, return_logits=True, prefill_chunk_size=chunk)
+    assert torch.equal(g0, g1)
+    if exact:
+        assert torch.equal(l0, l1)
+    else:
+        assert (l0 - l1).abs().max().item() <= 0.03 * l0.std().item()

@@ -62,6 +62,29 @@ def test_gather_tokens_gloo_world2(counts):
     mp.spawn(_gather_worker, args=(2, _free_port(), counts), nprocs=2, join=True)
 
 
+def _gather_ragged_worker(rank, world, port):
+    """Rank 0 stopped early on EOS (5 columns, 2 rows), rank 1 ran to the end (9 columns, 3 rows): the collective must see
+    equal shapes (mismatched L hangs / corrupts NCCL) and the short shard comes back right-padded."""
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rows, L = [(2, 5), (3, 9)][rank]
+    local = torch.arange(rows * L, dtype=torch.int64).view(rows, L) + 1000 * (rank + 1)
+    out = gather_tokens(local, [2, 3], pad_token_id=77)
+    exp0 = torch.full((2, 9), 77, dtype=torch.int64)
+    exp0[:, :5] = torch.arange(10, dtype=torch.int64).view(2, 5) + 1000
+    exp1 = torch.arange(27, dtype=torch.int64).view(3, 9) + 2000
+    assert torch.equal(out, torch.cat([exp0, exp1])), (rank, out)
+    dist.destroy_process_group()
+
+
+def test_gather_tokens_ragged_lengths_gloo_world2():
+    import torch.multiprocessing as mp
+
+    mp.spawn(_gather_ragged_worker, args=(2, _free_port()), nprocs=2, join=True)
+
+
 def test_gather_identity_without_process_group():
     t = torch.arange(6).view(2, 3)
     assert gather_tokens(t) is t
@@ -144,4 +167,71 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert d["e2e"] == {"value": d["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     cb = d["cpu_baseline"]
     assert cb["kind"] == "reference" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["dtype"] in ("bf16", "fp32")
-    assert set(cb["dtype_probe_ms"]) == {"bf16", "fp32"} and "cpu_model" in cb["host"] and "sample" in cb
+    assert cb["dtype_rule"]["rule"] == "ISA flags" and "cpu_model" in cb["host"] and "sample" in cb
+    assert "4/28 decoder layers" in cb["sample"]            # >= 4 sampled layers, fixed thread count
+
+
+def test_own_mel_filterbank_is_bit_identical_to_the_reference_table():
+    """a2 of SURVEY 8-a: the product builds the 201 x 128 slaney filterbank itself; it must equal, bit for bit, the table the
+    reference builds ([O] WFE:95-103 -> AU:453-544).  Only this test imports the reference generator."""
+    from transformers.audio_utils import mel_filter_bank
+
+    from audio_flamingo_b200.processing import slaney_mel_filterbank
+
+    ref = mel_filter_bank(num_frequency_bins=201, num_mel_filters=128, min_frequency=0.0, max_frequency=8000.0, sampling_rate=16000,
+                          norm="slaney", mel_scale="slaney")
+    ours = slaney_mel_filterbank(128, 201, 8000.0)
+    assert ours.dtype == ref.dtype == np.float64 and ours.shape == ref.shape == (201, 128)
+    assert np.array_equal(ours, ref)
+
+
+def test_product_does_not_import_reference_package_for_constants():
+    import pathlib
+
+    src = (pathlib.Path(__file__).resolve().parent.parent / "audio_flamingo_b200" / "processing.py").read_text()
+    assert "transformers" not in src.replace("transformers.audio_utils.mel_filter_bank(201", "")  # the docstring names it once
+
+
+def test_music_flamingo_timestamps_match_reference_index_arithmetic():
+    """Own, sync-free formulation of the frame start times vs the reference's ([O] modular_musicflamingo.py:250-285), on prompts
+    with one run spanning two windows, two runs in one row, and a run touching the row end."""
+    from transformers.models.musicflamingo.modeling_musicflamingo import MusicFlamingoForConditionalGeneration as HF
+
+    from audio_flamingo_b200.modeling import MusicFlamingoForConditionalGeneration as Ours
+
+    class Cfg:
+        audio_token_id = 7
+        audio_frame_step = 0.01
+
+    class Holder:
+        config = Cfg()
+        _mf_frame_step = 0.01
+
+    cases = [
+        (torch.tensor([[1, 1, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 2, 2, 2, 2], [3, 7, 7, 7, 4, 7, 7, 7, 7, 7, 5, 5, 5, 5, 5, 5]]), [6, 4, 3, 5]),
+        (torch.tensor([[0, 0, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7], [5, 5, 5, 5, 5, 5, 5, 5, 5, 7, 7, 7, 7, 7]]), [5, 5, 2, 5]),
+        (torch.tensor([[7, 7, 7, 1]]), [3]),
+    ]
+    for ids, post in cases:
+        post = torch.tensor(post)
+        ref = HF._build_audio_timestamps(Holder(), ids, post, 8).float()
+        ours = Ours._build_audio_timestamps(Holder(), ids, post, 8)
+        assert ours.dtype == torch.float32 and torch.equal(ours, ref), (ids, ours[:, 0], ref[:, 0])
+
+
+def test_kv_cache_grows_like_dynamic_cache():
+    """forward(use_cache=True) reserves room for a continuation and the cache grows on demand (a zero reserve made the
+    first cached step write past the allocation): capacity buckets, live rows preserved, rows beyond stay zero."""
+    from audio_flamingo_b200.modeling import AF3KVCache
+
+    assert [AF3KVCache.bucket(n) for n in (0, 1, 256, 257, 781, 908)] == [256, 256, 256, 512, 1024, 1024]
+    c = AF3KVCache(n_layers=2, B=2, Hkv=1, Tmax=256, D=4, device="cpu")
+    c.k[:, :, :, :200] = 1.0
+    c.v[:, :, :, :200] = 2.0
+    c.length = 200
+    c.ensure_capacity(256)
+    assert c.Tmax == 256
+    c.ensure_capacity(257)
+    assert c.Tmax == 512 and c.k.shape == (2, 2, 1, 512, 4) and c.length == 200
+    assert bool((c.k[:, :, :, :200] == 1).all()) and bool((c.v[:, :, :, :200] == 2).all())
+    assert not c.k[:, :, :, 200:].any() and not c.v[:, :, :, 200:].any()

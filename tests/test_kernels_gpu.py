@@ -358,9 +358,11 @@ def test_logmel_vs_fp64(ops):
     assert err.max() < 1e-4, err.max()
 
 
-def test_qkv_rope_fused_gemm_matches_unfused(ops):
-    """Decode-step fusion: q/k/v projection + RoPE + KV append in the GEMM epilogue == GEMM then af3_rope_kv_append."""
-    B, H, Hkv, D, K, Tmax, slot = 32, 28, 4, 128, 512, 64, 37
+@pytest.mark.parametrize("B", [32, 5, 48, 64])
+def test_qkv_rope_fused_gemm_matches_unfused(ops, B):
+    """Decode-step fusion: q/k/v projection + RoPE + KV append in the GEMM epilogue == GEMM then af3_rope_kv_append
+    (up to 64 sequences: two 32-token column tiles)."""
+    H, Hkv, D, K, Tmax, slot = 28, 4, 128, 512, 64, 37
     x, w, b = _rand((B, K), 1.0, 60), _rand(((H + 2 * Hkv) * D, K), 0.05, 61), _rand(((H + 2 * Hkv) * D,), 0.3, 62)
     inv_freq = (1.0 / (1e6 ** (torch.arange(0, D, 2, dtype=torch.int64).float() / D))).cuda()
     starts = torch.randint(0, 30, (B,), dtype=torch.int32).cuda()
@@ -373,3 +375,26 @@ def test_qkv_rope_fused_gemm_matches_unfused(ops):
     qkv2 = ops.qkv_rope_linear(x, w, b, kc2, vc2, H=H, Hkv=Hkv, D=D, rope_cs=cs, pos_dev=pos)
     assert torch.equal(qkv2[:, :H * D], qkv1[:, :H * D])
     assert torch.equal(kc2, kc1) and torch.equal(vc2, vc1)
+
+
+def test_qkv_rope_fused_gemm_never_writes_past_the_cache(ops):
+    """with the cache full (slot == Tmax) the fused epilogue must drop the append instead of writing into the next
+    (sequence, head) / past the allocation; the query heads are still produced."""
+    B, H, Hkv, D, K, Tmax = 4, 28, 4, 128, 256, 16
+    x, w, b = _rand((B, K), 1.0, 70), _rand(((H + 2 * Hkv) * D, K), 0.05, 71), _rand(((H + 2 * Hkv) * D,), 0.3, 72)
+    inv_freq = (1.0 / (1e6 ** (torch.arange(0, D, 2, dtype=torch.int64).float() / D))).cuda()
+    guard = torch.full((2, B, Hkv, Tmax + 8, D), 7.0, device="cuda", dtype=bf16)   # 8 guard rows behind every (seq, head) block
+    kc, vc = guard[0, :, :, :Tmax], guard[1, :, :, :Tmax]
+    kc_c, vc_c = kc.contiguous(), vc.contiguous()                                  # the kernel takes dense [B, Hkv, Tmax, D] caches
+    pos = torch.tensor([Tmax], dtype=torch.int32, device="cuda")
+    cs = ops.rope_table(B, D, pos, None, inv_freq)
+    before_k, before_v = kc_c.clone(), vc_c.clone()
+    q = ops.qkv_rope_linear(x, w, b, kc_c, vc_c, H=H, Hkv=Hkv, D=D, rope_cs=cs, pos_dev=pos)
+    torch.cuda.synchronize()
+    assert torch.equal(kc_c, before_k) and torch.equal(vc_c, before_v)
+    assert torch.isfinite(q[:, : H * D].float()).all()
+    # the stand-alone append kernel with a device-side position has the same guard
+    qkv = ops.linear(x, w, b)
+    ops.rope_kv_append(qkv, kc_c, vc_c, B=B, T=1, H=H, Hkv=Hkv, D=D, pos0=0, inv_freq=inv_freq, pos0_dev=pos)
+    torch.cuda.synchronize()
+    assert torch.equal(kc_c, before_k) and torch.equal(vc_c, before_v)

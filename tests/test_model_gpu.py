@@ -34,7 +34,7 @@ def test_forward_logits_and_audio_features(O, preset, secs):
     cfg = ref32.config
     waves, feats, fmask, ids, am = _inputs(O, cfg, secs)
     ours = AudioFlamingo3ForConditionalGeneration.from_reference(ref32, device="cuda")
-    ref16 = O.hf_model(preset, seed=0, sharpen=8.0).to("cuda", bf16)
+    ref16 = O.hf_restore_fp32_rotary(O.hf_model(preset, seed=0, sharpen=8.0).to("cuda", bf16))
     with torch.no_grad():
         l32 = ref32(input_ids=ids, attention_mask=am, input_features=feats, input_features_mask=fmask).logits
         l16 = ref16(input_ids=ids.cuda(), attention_mask=am.cuda(), input_features=feats.cuda().to(bf16),
@@ -69,7 +69,7 @@ def test_generate_greedy_ids(O, preset, secs, new):
     cfg = ref32.config
     waves, feats, fmask, ids, am = _inputs(O, cfg, secs, seed=5)
     ours = AudioFlamingo3ForConditionalGeneration.from_reference(ref32, device="cuda")
-    ref16 = ref32.to("cuda", bf16)
+    ref16 = O.hf_restore_fp32_rotary(ref32.to("cuda", bf16))
     with torch.no_grad():
         g_ref = ref16.generate(input_ids=ids.cuda(), attention_mask=am.cuda(), input_features=feats.cuda().to(bf16),
                                input_features_mask=fmask.cuda(), max_new_tokens=new, do_sample=False)
