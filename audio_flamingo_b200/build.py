@@ -21,6 +21,7 @@ SOURCES = [
     "common.cu",
     "gemm_tcgen05.cu",
     "attention_tcgen05.cu",
+    "attention_v2_tcgen05.cu",
     "decode_attention.cu",
     "elementwise.cu",
     "logmel.cu",

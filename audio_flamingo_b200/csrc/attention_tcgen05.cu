@@ -10,6 +10,8 @@
 //              exp2 / row sum / bf16 P written into the swizzled smem layout the UMMA descriptor expects),
 //              O stays in TMEM and is rescaled lazily (only when the running max grew by > 2^8, FA-style).
 // Scores never touch HBM; HBM traffic is Q + K + V + O once per (batch, head) (K/V re-reads hit L2).
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "common.h"
@@ -392,6 +394,10 @@ static int launch_attention(cudaStream_t stream, const CUtensorMap& mq, const CU
     return 0;
 }
 
+int attention_v2(cudaStream_t stream, const bf16* q, int ldq, const bf16* k, const bf16* v, int ldk, int kv_layout,
+                 int Tk_pitch, bf16* out, int ldo, int B, int H, int Hkv, int D, int Tq, int Tk, float scale, int causal,
+                 const int* kv_len, const int* kv_start);
+
 int attention(cudaStream_t stream, const bf16* q, int ldq, const bf16* k, const bf16* v, int ldk, int kv_layout,
               int Tk_pitch, bf16* out, int ldo, int B, int H, int Hkv, int D, int Tq, int Tk, float scale, int causal,
               const int* kv_len, const int* kv_start) {
@@ -399,6 +405,14 @@ int attention(cudaStream_t stream, const bf16* q, int ldq, const bf16* k, const 
     AF3_REQUIRE(H % Hkv == 0, "attention: H must be a multiple of Hkv");
     AF3_REQUIRE(ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "attention: output must be 16-byte aligned");
     if (B <= 0 || Tq <= 0) return 0;
+    // round-2 kernel (two Q tiles per CTA, P in TMEM; attention_v2_tcgen05.cu) unless AF3_ATTN_V1=1 asks for the round-1
+    // kernel below (kept for A/B measurements and as the parity cross-check of the new one; read per call)
+    {
+        const char* e = getenv("AF3_ATTN_V1");
+        if (!(e && e[0] == '1'))
+            return attention_v2(stream, q, ldq, k, v, ldk, kv_layout, Tk_pitch, out, ldo, B, H, Hkv, D, Tq, Tk, scale, causal, kv_len,
+                                kv_start);
+    }
     AttnArgs a{};
     a.Tq = Tq;
     a.Tk = Tk;

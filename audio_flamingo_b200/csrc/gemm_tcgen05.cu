@@ -268,6 +268,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
                     tma_load_2d(epi_stage + (q * 2 + b0) * 4096, &map_res, &rbar[q * 2 + b0], out_col_base, row0);
                 }
             }
+            // few-token mode with a fused residual: this thread's residual vectors of the transposed epilogue (token et / 4,
+            // features (et % 4) * 32 ...) do not depend on this GEMM -- request them now, they arrive while the weights stream
+            // (the epilogue otherwise exposes one more L2 round trip in the split-K tail, profiles/r02a_timeline_base.md)
+            [[maybe_unused]] uint4 rv_pre[4];
+            [[maybe_unused]] bool rv_ok = false;
+            if constexpr (SWAP && BN == 32 && NA == 1) {
+                if ((flags & EPI_RESID) && !(flags & EPI_F32OUT) && (a.ldo & 7) == 0 && (a.ld_res & 7) == 0 && a.res_period == 0) {
+                    const int et = threadIdx.x - 64;
+                    const int tok = c * BN + (et >> 2);
+                    const int f0 = r * 128 + (et & 3) * 32;
+                    if (tok < a.n_tok) {
+                        rv_ok = true;
+                        const uint4* rp = reinterpret_cast<const uint4*>(a.resid + static_cast<size_t>(tok) * a.ld_res + f0);
+#pragma unroll
+                        for (int g4 = 0; g4 < 4; ++g4) rv_pre[g4] = (f0 + g4 * 8 < a.n_feat) ? __ldcg(rp + g4) : make_uint4(0, 0, 0, 0);
+                    }
+                }
+            }
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             if (threadIdx.x == 64) trace_mark(a.trace, 2);
@@ -501,23 +519,39 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
                             float* wt = a.ws + (static_cast<size_t>(tile) * k_splits) * (BN * 128);
 #pragma unroll
                             for (int j = 0; j < 32; ++j) wt[(sp * BN + j) * 128 + row_in_tile] = __uint_as_float(v[j]);
-                            __threadfence();
+                            // release: the barrier orders every thread's partial stores before thread 64's fence + counter
+                            // increment (fences are cumulative -- the cooperative-groups grid-sync pattern); acquire: thread 64's
+                            // fence after the increment, then the barrier, then L2 (.cg) loads by everyone
                             asm volatile("bar.sync 1, 128;" ::: "memory");
-                            if (threadIdx.x == 64) *reinterpret_cast<volatile int*>(tmem_slot + 1) = atomicAdd(a.counters + tile, 1);
+                            if (threadIdx.x == 64) {
+                                __threadfence();
+                                const int arrived_now = atomicAdd(a.counters + tile, 1);
+                                __threadfence();
+                                *reinterpret_cast<volatile int*>(tmem_slot + 1) = arrived_now;
+                            }
                             asm volatile("bar.sync 1, 128;" ::: "memory");
                             const int arrived = *reinterpret_cast<volatile int*>(tmem_slot + 1);
                             if (arrived != k_splits - 1) continue;  // not the last split of this tile: done
-                            __threadfence();
-                            // fixed split order (deterministic); 32 independent L2 loads in flight per round
-                            float sum[32];
+                            // Sum in split order (deterministic, same order as ever: 0, 1, 2, ...).  Two register buffers keep the
+                            // loads of split s + 1 (and s + 2) in flight while split s is added: the k_splits dependent L2 round
+                            // trips of round 1 (5 x ~0.7 us in the down / o projections' tails) become ~k_splits / 2.
+                            float sum[32], ta[32], tb[32];
+                            auto ld_part = [&](float (&d)[32], int s2) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) d[j] = __ldcg(wt + (s2 * BN + j) * 128 + row_in_tile);
+                            };
+                            ld_part(ta, 0);
 #pragma unroll
                             for (int j = 0; j < 32; ++j) sum[j] = 0.f;
-                            for (int s2 = 0; s2 < k_splits; ++s2) {
-                                float tmp[32];
+                            for (int s2 = 0; s2 < k_splits; s2 += 2) {
+                                if (s2 + 1 < k_splits) ld_part(tb, s2 + 1);
 #pragma unroll
-                                for (int j = 0; j < 32; ++j) tmp[j] = __ldcg(wt + (s2 * BN + j) * 128 + row_in_tile);
+                                for (int j = 0; j < 32; ++j) sum[j] += ta[j];
+                                if (s2 + 2 < k_splits) ld_part(ta, s2 + 2);
+                                if (s2 + 1 < k_splits) {
 #pragma unroll
-                                for (int j = 0; j < 32; ++j) sum[j] += tmp[j];
+                                    for (int j = 0; j < 32; ++j) sum[j] += tb[j];
+                                }
                             }
 #pragma unroll
                             for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(sum[j]);
@@ -592,10 +626,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
                                 bf16* op = reinterpret_cast<bf16*>(a.out) + static_cast<size_t>(tok) * a.ldo + f0;
                                 uint4 rv[4];
                                 if (flags & EPI_RESID) {
-                                    const uint4* rp = reinterpret_cast<const uint4*>(a.resid + static_cast<size_t>(tok) * a.ld_res + f0);
+                                    if constexpr (NA == 1) {
+                                        if (rv_ok) {   // requested before the accumulator wait (same token / features: ch == 0 for BN = 32)
 #pragma unroll
-                                    for (int g4 = 0; g4 < 4; ++g4)
-                                        if (f0 + g4 * 8 < a.n_feat) rv[g4] = __ldcg(rp + g4);
+                                            for (int g4 = 0; g4 < 4; ++g4) rv[g4] = rv_pre[g4];
+                                        }
+                                    } else {
+                                        const uint4* rp = reinterpret_cast<const uint4*>(a.resid + static_cast<size_t>(tok) * a.ld_res + f0);
+#pragma unroll
+                                        for (int g4 = 0; g4 < 4; ++g4)
+                                            if (f0 + g4 * 8 < a.n_feat) rv[g4] = __ldcg(rp + g4);
+                                    }
                                 }
 #pragma unroll
                                 for (int g4 = 0; g4 < 4; ++g4) {
@@ -826,7 +867,7 @@ int gemm_bf16(cudaStream_t stream, const bf16* x, int ldx, const bf16* w, int ld
     const int kb_total = ceil_div(K, BK);
     if (workspace && workspace_bytes >= gemm_workspace_bytes() && tiles * 2 <= sm_count() && tiles <= 4096) {
         int s = sm_count() / tiles;
-        static const int forced = [] { const char* e = getenv("AF3_KSPLIT"); return e ? atoi(e) : 0; }();  // experiments only
+        const int forced = [] { const char* e = getenv("AF3_KSPLIT"); return e ? atoi(e) : 0; }();  // experiments only (read per call)
         if (forced > 0) s = forced;
         if (s > kb_total / 4) s = kb_total / 4;  // keep at least 4 k-blocks per split
         if (s > 16) s = 16;

@@ -26,14 +26,18 @@ def shard_rows(n_rows: int, world_size: int, rank: int, weights: list[int] | Non
     if len(weights) != n_rows:
         raise ValueError("weights must have one entry per row")
     total = sum(weights)
-    cuts, acc, r = [0], 0, 1
-    for i, w in enumerate(weights):
-        acc += w
-        while r < world_size and acc * world_size >= r * total and len(cuts) <= r:
-            cuts.append(i + 1)
-            r += 1
-    while len(cuts) < world_size:
-        cuts.append(n_rows)
+    prefix = [0]
+    for w in weights:
+        prefix.append(prefix[-1] + w)
+    # boundary r goes where the cumulative weight is CLOSEST to r/world of the total (ties: the earlier row), never before the
+    # previous boundary: every shard ends within half a sequence of its ideal load
+    cuts = [0]
+    for r in range(1, world_size):
+        best = cuts[-1]
+        for i in range(cuts[-1], n_rows + 1):
+            if abs(prefix[i] * world_size - r * total) < abs(prefix[best] * world_size - r * total):
+                best = i
+        cuts.append(best)
     cuts.append(n_rows)
     return cuts[rank], cuts[rank + 1]
 
@@ -75,3 +79,34 @@ def gather_tokens(local_tokens: torch.Tensor, counts: list[int] | None = None, g
     if all(c == mx for c in counts):
         return out
     return torch.cat([out[r * mx: r * mx + counts[r]] for r in range(world)], 0)
+
+
+def kv_bytes_per_token(n_layers: int, n_kv_heads: int, head_dim: int, dtype_bytes: int = 2) -> int:
+    """K + V bytes one cached token costs per sequence (AF3-7B: 28 x 4 x 128 x 2 B x 2 = 57 344 B)."""
+    return 2 * n_layers * n_kv_heads * head_dim * dtype_bytes
+
+
+def plan_kv_capacity(prompt_lens: list[int], max_new_tokens: int, *, n_layers: int, n_kv_heads: int, head_dim: int,
+                     hbm_free_bytes: int, activation_bytes_per_token: int = 0, prefill_chunk_size: int | None = None,
+                     bucket: int = 256) -> dict:
+    """Capacity planning for long-audio batches (up to 20 windows -> 15 000 audio tokens per sequence,
+    0.86 GB of KV cache each): how many of the given prompts fit one GPU at once, and what the batch costs.
+
+    The cache is one [B, Hkv, Tmax, D] block per layer with Tmax = the longest (prompt + max_new_tokens) rounded up to `bucket`
+    rows (generate()'s capacity rule), so a batch costs B * Tmax * kv_bytes_per_token.  Prefill activations scale with the number
+    of prompt rows in flight: B * min(S, prefill_chunk_size) * activation_bytes_per_token (pass the model's figure: for AF3-7B
+    about (3584 * 4 + 2 * 18944 + 4608) * 2 B = 115 kB per token with the fused SwiGLU path).
+    Returns {"fits", "max_batch", "tmax", "kv_bytes", "activation_bytes", "bytes_per_sequence"}: max_batch counts how many
+    sequences as long as the LONGEST one fit, i.e. a safe per-GPU batch for this length class.
+    """
+    if not prompt_lens:
+        return {"fits": True, "max_batch": 0, "tmax": 0, "kv_bytes": 0, "activation_bytes": 0, "bytes_per_sequence": 0}
+    S = max(prompt_lens)
+    tmax = -(-(S + max_new_tokens) // bucket) * bucket
+    per_tok = kv_bytes_per_token(n_layers, n_kv_heads, head_dim)
+    rows_in_flight = min(S, prefill_chunk_size) if prefill_chunk_size else S
+    per_seq = tmax * per_tok + rows_in_flight * activation_bytes_per_token
+    B = len(prompt_lens)
+    return {"fits": B * per_seq <= hbm_free_bytes, "max_batch": int(hbm_free_bytes // per_seq) if per_seq else 0, "tmax": tmax,
+            "kv_bytes": B * tmax * per_tok, "activation_bytes": B * rows_in_flight * activation_bytes_per_token,
+            "bytes_per_sequence": per_seq}

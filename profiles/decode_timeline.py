@@ -26,13 +26,6 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 
-def kind_name(key):
-    kind, a, b, c, flags = key
-    if kind == "gemm":
-        return f"gemm {b}x{c}" + (" +rope" if flags & 32 else "") + (" swiglu" if flags & 8 else "")
-    return kind
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=str(ROOT / "profiles" / "r02_decode_timeline"))
@@ -44,7 +37,7 @@ def main():
     args = ap.parse_args()
 
     import bench
-    from audio_flamingo_b200 import AudioFlamingo3ForConditionalGeneration, _lib, ops
+    from audio_flamingo_b200 import AudioFlamingo3ForConditionalGeneration
 
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
@@ -59,83 +52,25 @@ def main():
     ids = torch.from_numpy(rs.randint(1, 151643, size=(args.batch, args.prompt)).astype(np.int64)).to(dev)
     am = torch.ones_like(ids)
 
-    lib = _lib.load()
-    slot_words = lib.af3_trace_slot_bytes() // 8
-    n_slots = 4096
-    buf = torch.zeros((n_slots * slot_words,), device=dev, dtype=torch.int64)
+    from audio_flamingo_b200.trace import DecodeTrace
 
     # warm run without tracing (configures kernels, allocator), state dropped so the traced run captures a fresh graph
     model.generate(input_ids=ids, attention_mask=am, max_new_tokens=4)
     model.release_decode_state()
     torch.cuda.synchronize()
 
-    ops.TRACE_LOG = []
-    lib.af3_trace_begin(buf.data_ptr(), buf.numel() * 8)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     model.stage_events = []
-    model.generate(input_ids=ids, attention_mask=am, max_new_tokens=args.new_tokens)
-    torch.cuda.synchronize()
-    n_rec = lib.af3_trace_end()
-    log, ops.TRACE_LOG = ops.TRACE_LOG, None
+    with DecodeTrace(dev) as tr:
+        model.generate(input_ids=ids, attention_mask=am, max_new_tokens=args.new_tokens)
+    n_rec = tr.n_recorded
     ev = dict(model.stage_events)
     decode_ms = ev["prefill_done"].elapsed_time(ev["decode_done"])
     model.stage_events = None
-
-    cap = [e for e in log if e[0] == "graph_capture"]
-    assert cap, "the decode step was not captured (max_new_tokens too small?)"
-    _, i0, i1 = cap[-1]
-    entries = [e for e in log[i0:i1] if e[0] != "graph_capture"]
-    raw = buf.view(n_slots, -1, 4).cpu().numpy().astype(np.int64)  # [slot][cta][mark]
-
-    launches = []
-    for key, s0, s1 in entries:
-        for s in range(s0, s1):
-            if s >= n_slots:
-                continue
-            m = raw[s]
-            live = m[:, 0] > 0
-            if not live.any():
-                continue
-            rec = {"slot": s, "kind": kind_name(key) + (f" #{s - s0}" if s1 - s0 > 1 else ""), "ctas": int(live.sum()),
-                   "entry_min": int(m[live, 0].min()), "entry_max": int(m[live, 0].max()),
-                   "wait_min": int(m[live, 1][m[live, 1] > 0].min()) if (m[live, 1] > 0).any() else None,
-                   "wait_max": int(m[live, 1].max()) or None,
-                   "mid_max": int(m[live, 2].max()) or None,
-                   "exit_min": int(m[live, 3][m[live, 3] > 0].min()) if (m[live, 3] > 0).any() else None,
-                   "exit_max": int(m[live, 3].max()) or None}
-            launches.append(rec)
-    launches.sort(key=lambda r: r["entry_min"])
-    t0 = launches[0]["entry_min"]
-    for r in launches:
-        for k in ("entry_min", "entry_max", "wait_min", "wait_max", "mid_max", "exit_min", "exit_max"):
-            if r[k] is not None:
-                r[k] = (r[k] - t0) / 1e3  # us since the step's first kernel entry
-    step_us = launches[-1]["exit_max"] - launches[0]["entry_min"]
-
-    # per launch: lead = how long before its dependency resolved the kernel was already resident (pre-wait prefetch window),
-    # body = dependency resolved -> last CTA exit, gap = predecessor's last exit -> this kernel's dependency resolved
-    agg = {}
-    prev_exit = None
-    for r in launches:
-        name = r["kind"]
-        a = agg.setdefault(name, {"n": 0, "lead_us": 0.0, "body_us": 0.0, "stream_us": 0.0, "tail_us": 0.0, "gap_us": 0.0})
-        a["n"] += 1
-        if r["wait_max"] is not None and r["exit_max"] is not None:
-            r["lead_us"] = r["wait_min"] - r["entry_min"]
-            r["body_us"] = r["exit_max"] - r["wait_min"]
-            a["lead_us"] += r["lead_us"]
-            a["body_us"] += r["body_us"]
-            if r["mid_max"] is not None:
-                a["stream_us"] += r["mid_max"] - r["wait_min"]
-                a["tail_us"] += r["exit_max"] - r["mid_max"]
-            if prev_exit is not None:
-                r["gap_us"] = r["wait_min"] - prev_exit
-                a["gap_us"] += r["gap_us"]
-        prev_exit = r["exit_max"] if r["exit_max"] is not None else prev_exit
-    for a in agg.values():
-        for k in list(a):
-            if k != "n":
-                a[k] = round(a[k], 2)
+    launches = tr.graph_launches()
+    assert launches, "the decode step was not captured (max_new_tokens too small?)"
+    model.release_decode_state()   # the captured graph writes into tr.buf: drop it before the buffer goes away
+    step_us = max(r["exit_max"] for r in launches if r["exit_max"] is not None) - launches[0]["entry_min"]
+    agg = DecodeTrace.aggregate(launches)
 
     out = {"tag": args.tag, "env": {k: v for k, v in os.environ.items() if k.startswith("AF3_")},
            "shape": {"batch": args.batch, "prompt": args.prompt, "layers": args.layers, "new_tokens": args.new_tokens},
@@ -146,10 +81,14 @@ def main():
     lines = [f"# decode-step timeline ({args.tag}): {step_us:.1f} us per step from the trace, "
              f"{decode_ms / (args.new_tokens - 1) * 1e3:.1f} us per step by CUDA events over the decode stage", "",
              f"env: {out['env']}", "",
-             "| kernel | launches | body us (dep. resolved -> last exit) | stream us (-> accumulators ready) | tail us | resident before dep. us | gap after predecessor us |",
-             "|---|---|---|---|---|---|---|"]
-    for name, a in sorted(agg.items(), key=lambda kv: -kv[1]["body_us"]):
-        lines.append(f"| {name} | {a['n']} | {a['body_us']:.1f} | {a['stream_us']:.1f} | {a['tail_us']:.1f} | {a['lead_us']:.1f} | {a['gap_us']:.1f} |")
+             "Sums over the launches of one step, in us.  slot = last exit - predecessor's last exit (exclusive share of the step; the slots add up "
+             "to the step); body = dependency resolved -> last exit; stream = -> last accumulator ready; tail = rest of the body; resident "
+             "before dep. = time the kernel sat resident ahead of its dependency (pre-wait weight prefetch window); gap = predecessor's last "
+             "exit -> dependency resolved.", "",
+             "| kernel | launches | slot | body | stream | tail | resident before dep. | gap after predecessor |",
+             "|---|---|---|---|---|---|---|---|"]
+    for name, a in sorted(agg.items(), key=lambda kv: -kv[1]["slot_us"]):
+        lines.append(f"| {name} | {a['n']} | {a['slot_us']:.1f} | {a['body_us']:.1f} | {a['stream_us']:.1f} | {a['tail_us']:.1f} | {a['lead_us']:.1f} | {a['gap_us']:.1f} |")
     lines += ["", "First layer in launch order (us since step start):", "",
               "| kernel | ctas | entry min..max | dep. resolved min..max | main loop done | exit min..max |", "|---|---|---|---|---|---|"]
     for r in launches[:12]:

@@ -235,3 +235,22 @@ def test_kv_cache_grows_like_dynamic_cache():
     assert c.Tmax == 512 and c.k.shape == (2, 2, 1, 512, 4) and c.length == 200
     assert bool((c.k[:, :, :, :200] == 1).all()) and bool((c.v[:, :, :, :200] == 2).all())
     assert not c.k[:, :, :, 200:].any() and not c.v[:, :, :, 200:].any()
+
+
+def test_kv_capacity_planning_long_audio():
+    """a 10-minute clip = 20 windows = 15 000 audio tokens; AF3-7B costs 57 344 B of KV per token per sequence."""
+    from audio_flamingo_b200.sharding import kv_bytes_per_token, plan_kv_capacity, shard_rows
+
+    assert kv_bytes_per_token(28, 4, 128) == 57344
+    geo = dict(n_layers=28, n_kv_heads=4, head_dim=128)
+    p = plan_kv_capacity([15030] * 4, 128, hbm_free_bytes=140 << 30, activation_bytes_per_token=115_000, **geo)
+    assert p["tmax"] == 15360 and p["kv_bytes"] == 4 * 15360 * 57344            # 0.88 GB per sequence, the survey's 0.86 GB + bucket
+    assert p["fits"] and p["max_batch"] == (140 << 30) // (15360 * 57344 + 15030 * 115_000)
+    chunked = plan_kv_capacity([15030] * 4, 128, hbm_free_bytes=140 << 30, activation_bytes_per_token=115_000, prefill_chunk_size=2048, **geo)
+    assert chunked["max_batch"] > p["max_batch"] and chunked["activation_bytes"] == 4 * 2048 * 115_000
+    assert not plan_kv_capacity([15030] * 200, 128, hbm_free_bytes=140 << 30, **geo)["fits"]
+    # ragged long-audio batch: balance the shards by WINDOW count, all windows of a sequence on one rank (SURVEY 8-e)
+    windows = [20, 1, 1, 2, 20, 3, 1, 12]
+    spans = [shard_rows(len(windows), 2, r, windows) for r in range(2)]
+    loads = [sum(windows[a:b]) for a, b in spans]
+    assert spans[0][1] == spans[1][0] and abs(loads[0] - loads[1]) <= max(windows)

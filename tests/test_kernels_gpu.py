@@ -190,8 +190,17 @@ def _sdpa_ref(q, k, v, scale, mask):
     return p @ v
 
 
-@pytest.mark.parametrize("D,H,T,lens", [(64, 4, 200, None), (64, 20, 1500, None), (64, 3, 333, [333, 100, 7]), (128, 2, 256, None)])
-def test_attention_bidirectional(ops, D, H, T, lens):
+@pytest.fixture(params=["v2", "v1"])
+def attn_impl(request, monkeypatch):
+    """Both generations of the prefill / encoder attention kernel go through the same parity cases: v2 (two Q tiles per CTA,
+    P in tensor memory; the default) and the round-1 kernel (AF3_ATTN_V1=1, kept as its cross-check)."""
+    monkeypatch.setenv("AF3_ATTN_V1", "1" if request.param == "v1" else "0")
+    return request.param
+
+
+@pytest.mark.parametrize("D,H,T,lens", [(64, 4, 200, None), (64, 20, 1500, None), (64, 3, 333, [333, 100, 7]), (128, 2, 256, None),
+                                        (64, 2, 1500, [1500, 385, 12]), (128, 3, 700, [700, 129, 256])])
+def test_attention_bidirectional(ops, attn_impl, D, H, T, lens):
     B = 3 if lens else 2
     qkv = _rand((B * T, 3 * H * D), 1.0, 40)
     out = torch.zeros((B * T, H * D), device="cuda", dtype=bf16)
@@ -208,9 +217,9 @@ def test_attention_bidirectional(ops, D, H, T, lens):
     _close(out, ref, 2e-2, 2e-2, f"attention D={D} T={T}")
 
 
-@pytest.mark.parametrize("T,starts", [(256, None), (300, [0, 37, 250]), (130, [5, 129])])
-def test_attention_causal_gqa_cache(ops, T, starts):
-    H, Hkv, D, Tmax = 8, 2, 128, 512
+@pytest.mark.parametrize("T,starts", [(256, None), (300, [0, 37, 250]), (130, [5, 129]), (780, [0, 3, 530]), (1000, None)])
+def test_attention_causal_gqa_cache(ops, attn_impl, T, starts):
+    H, Hkv, D, Tmax = 8, 2, 128, 1024
     B = len(starts) if starts else 2
     qkv = _rand((B * T, (H + 2 * Hkv) * D), 1.0, 41)
     k_cache = torch.zeros((B, Hkv, Tmax, D), device="cuda", dtype=bf16)
@@ -398,3 +407,32 @@ def test_qkv_rope_fused_gemm_never_writes_past_the_cache(ops):
     ops.rope_kv_append(qkv, kc_c, vc_c, B=B, T=1, H=H, Hkv=Hkv, D=D, pos0=0, inv_freq=inv_freq, pos0_dev=pos)
     torch.cuda.synchronize()
     assert torch.equal(kc_c, before_k) and torch.equal(vc_c, before_v)
+
+
+def test_attention_v2_matches_v1_on_a_live_cache_offset(ops, monkeypatch):
+    """Continuation chunk (chunked prefill / next chat turn): Tq = 200 new rows against Tk = 650 cached + new keys, causal with the
+    (Tk - Tq) offset, GQA 28:4, left padding on one row.  The two kernel generations must agree to within bf16 output rounding, and
+    both with the fp32 restatement."""
+    B, H, Hkv, D, Tq, Tk, Tmax = 2, 28, 4, 128, 200, 650, 768
+    q = _rand((B * Tq, (H + 2 * Hkv) * D), 1.0, 90)
+    k_cache, v_cache = _rand((B, Hkv, Tmax, D), 1.0, 91), _rand((B, Hkv, Tmax, D), 1.0, 92)
+    k_cache[:, :, Tk:] = 0
+    v_cache[:, :, Tk:] = 0
+    kv_start = torch.tensor([0, 77], dtype=torch.int32, device="cuda")
+    outs = {}
+    for impl in ("0", "1"):
+        monkeypatch.setenv("AF3_ATTN_V1", impl)
+        out = torch.zeros((B * Tq, H * D), device="cuda", dtype=bf16)
+        ops.attention(q, k_cache, v_cache, out.view(B, Tq, H * D), B=B, H=H, Hkv=Hkv, D=D, Tq=Tq, Tk=Tk, scale=D ** -0.5, causal=True,
+                      kv_layout=1, Tk_pitch=Tmax, ldq=(H + 2 * Hkv) * D, ldk=D, kv_start=kv_start)
+        outs[impl] = out
+    qq = q[:, :H * D].float().view(B, Tq, H, D).transpose(1, 2)
+    kk = k_cache[:, :, :Tk].float().repeat_interleave(H // Hkv, dim=1)
+    vv = v_cache[:, :, :Tk].float().repeat_interleave(H // Hkv, dim=1)
+    qi = torch.arange(Tq, device="cuda")[:, None] + (Tk - Tq)
+    mask = (torch.arange(Tk, device="cuda")[None, :] <= qi)[None, None].repeat(B, 1, 1, 1)
+    mask[1, :, :, :77] = False
+    ref = _sdpa_ref(qq, kk, vv, D ** -0.5, mask).transpose(1, 2).reshape(B * Tq, H * D)
+    _close(outs["0"], ref, 2e-2, 2e-2, "v2 vs fp32")
+    _close(outs["1"], ref, 2e-2, 2e-2, "v1 vs fp32")
+    _close(outs["0"], outs["1"], 2 ** -6, 2e-3, "v2 vs v1")

@@ -25,9 +25,10 @@ import torch
 pytestmark = pytest.mark.gpu
 bf16 = torch.bfloat16
 ROOT = Path(__file__).resolve().parent.parent
+LOUD = (64, 4.0)   # (number of token ids, row scale) of the peaked LM head; None = flat head (the round-2 first run, see below)
 
 
-def _hf_model_on_gpu(O, cfg, seed, sharpen):
+def _hf_model_on_gpu(O, cfg, seed, sharpen, loud=None):
     """Unmodified HF AudioFlamingo3ForConditionalGeneration, bf16, weights drawn on the GPU (a CPU init of 8.3 B parameters takes
     minutes and 33 GB)."""
     from transformers import AudioFlamingo3ForConditionalGeneration
@@ -45,6 +46,14 @@ def _hf_model_on_gpu(O, cfg, seed, sharpen):
             else:
                 p.normal_(0.0, 0.02, generator=g)
         m.language_model.lm_head.weight.mul_(sharpen)
+        # a PEAKED output distribution, as a trained LM has: the rows of `loud[0]` token ids are scaled by loud[1].  With all
+        # 152 064 rows alike the logits are i.i.d. Gaussians whose typical top-2 gap (1.25 at sharpen 8) is BELOW the bf16 noise of the
+        # 60-layer stack (max |diff| 1.9 between HF-bf16 and ours, 2.6 between HF-bf16 and HF-fp32: profiles/parity_r02_flat_head.json),
+        # so greedy ids of two correct bf16 implementations -- or of HF with itself in fp32 -- differ within 32 steps on every
+        # row and token parity tests nothing.  The gap among K candidates relative to the noise on them scales like
+        # 1 / (eps * 2 ln K): K = 64 loud ids make most steps decisive without touching the geometry.
+        if loud is not None:
+            m.language_model.lm_head.weight[: loud[0]].mul_(loud[1])
     # rotary inv_freq is a non-persistent buffer: recompute after to_empty -- on the CPU, in fp32, as the reference's normal
     # loading path leaves it (from_pretrained(dtype=bf16) casts parameters, not this buffer; a blanket model.to(bf16) would round it)
     O.hf_restore_fp32_rotary(m)
@@ -62,7 +71,7 @@ def test_af3_7b_full_depth_parity_vs_hf_bf16_on_the_same_gpu():
     if free_gb < 100:
         pytest.skip(f"needs ~90 GB of HBM (two bf16 copies + one fp32 copy of AF3-7B), {free_gb:.0f} GB free")
     cfg = O.hf_config("af3-7b")
-    ref16 = _hf_model_on_gpu(O, cfg, seed=0, sharpen=8.0)
+    ref16 = _hf_model_on_gpu(O, cfg, seed=0, sharpen=8.0, loud=LOUD)
     ours = AudioFlamingo3ForConditionalGeneration.from_reference(ref16, device="cuda")
     secs = [30.0, 30.0, 22.5, 17.3, 12.0, 9.1, 5.5, 3.1]
     B, NEW = len(secs), 32
@@ -129,7 +138,8 @@ def test_af3_7b_full_depth_parity_vs_hf_bf16_on_the_same_gpu():
 
     report = {
         "what": "AF3-7B full depth (32 encoder + 28 decoder layers, full width), ours vs HF transformers bf16 on the same B200",
-        "weights": "seeded N(0,0.02) default-init family drawn on the GPU, lm_head x8 (sharpen), zero biases, unit norm gains",
+        "weights": "seeded N(0,0.02) default-init family drawn on the GPU, lm_head x8 (sharpen), zero biases, unit norm gains; "
+                   + (f"LM-head rows of the first {LOUD[0]} ids x{LOUD[1]} (peaked output distribution)" if LOUD else "flat LM head"),
         "batch": B, "clip_seconds": secs, "prompt_len": S, "new_tokens": NEW,
         "rows_identical_free_running": int(same.all(1).sum()), "rows": rows,
         "teacher_forced": {"steps": B * NEW, "argmax_agree": int(agree_tf.sum()), "decisive_steps": n_decisive,
@@ -151,7 +161,7 @@ def test_af3_7b_full_depth_parity_vs_hf_bf16_on_the_same_gpu():
     assert wrong_decisive == 0, f"{wrong_decisive} of {n_decisive} decisive steps disagree with the reference"
     # Gaussian logits over 152 064 ids put the typical top-2 gap at ~0.2 logit std, bf16 noise over 60 layers at ~0.1: a sizeable
     # share of steps is NOT decisive under the 2x rule and says nothing either way; the count is recorded, a floor keeps the test honest
-    assert n_decisive >= B * NEW // 8, f"only {n_decisive} of {B * NEW} steps are decisive: the comparison is close to vacuous"
+    assert n_decisive >= B * NEW // 4, f"only {n_decisive} of {B * NEW} steps are decisive: the comparison is close to vacuous"
     for r in rows:
         assert r["identical"] or not r["decisive"], f"free-running divergence on a decisive step: {r}"
     assert e_ours32 <= max(1.5 * e_ref32, 0.06 * std), (e_ours32, e_ref32, std)
