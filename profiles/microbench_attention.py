@@ -49,16 +49,20 @@ def prefill(B=32, H=28, Hkv=4, D=128, T=780, Tmax=1024):
 
 
 res = {}
+only_case, only_impl = os.environ.get("AF3_MB_CASE"), os.environ.get("AF3_MB_IMPL")   # ncu captures: one case, one kernel
 for name, mk in (("encoder_d64_t1500", encoder), ("prefill_d128_t780_causal", prefill), ("chat_prefill_d128_t3512_causal", lambda: prefill(B=2, T=3512, Tmax=3584))):
+    if only_case and only_case not in name:
+        continue
     fn, flops, out = mk()
     row = {}
     outs = {}
-    for impl in ("v1", "v2"):
+    for impl in ("v1", "v2") if not only_impl else (only_impl,):
         os.environ["AF3_ATTN_V1"] = "1" if impl == "v1" else "0"
         ms = timed(fn)
         row[impl] = {"ms": round(ms, 4), "tflops": round(flops / ms / 1e9, 1)}
         outs[impl] = out.float().clone()
-    row["speedup_v2_over_v1"] = round(row["v1"]["ms"] / row["v2"]["ms"], 3)
-    row["max_abs_diff_v2_v1"] = float((outs["v1"] - outs["v2"]).abs().max())
+    if not only_impl:
+        row["speedup_v2_over_v1"] = round(row["v1"]["ms"] / row["v2"]["ms"], 3)
+        row["max_abs_diff_v2_v1"] = float((outs["v1"] - outs["v2"]).abs().max())
     res[name] = row
 print(json.dumps(res, indent=1))

@@ -76,9 +76,18 @@ def test_generate_eos_rows_finish_at_different_steps(O, tiny):
     same_free = torch.equal(free_our, free_ref)
     print(f"free-running ids identical to the reference: {same_free}; distinct tokens per row: {[len(set(r.tolist())) for r in free_ref[:, S:]]}")
     g = free_ref[:, S:]
-    # (a) rows 0 / 1 stop at steps 2 / 9, row 2 unless it emits one of the two ids; (b) every row has an EOS id in its first 12
-    # tokens -> the loop stops early and the result is shorter; (c) a single int id
-    cands = [[int(g[0, 2]), int(g[1, 9])], [int(g[0, 2]), int(g[1, 9]), int(g[2, 11])], int(g[0, 2])]
+    # EOS ids are taken from what the rows actually emit (a tiny random LM may collapse onto one token): for every row the first
+    # token at a step >= 2 that the row has not emitted before, when there is one -> rows finish at different steps; plus ids that make
+    # EVERY row finish early (the loop must stop before max_new_tokens and cut the pads it had already enqueued), plus a single int
+    fresh = []
+    for b in range(g.shape[0]):
+        for t in range(2, new):
+            if int(g[b, t]) not in g[b, :t].tolist():
+                fresh.append(int(g[b, t]))
+                break
+    cands = [[int(g[b, min(3 * b + 1, new - 1)]) for b in range(g.shape[0])], int(g[0, 0])]
+    if fresh:
+        cands += [fresh, fresh[:1]]
     for eos in cands:
         with torch.no_grad():
             h = ref16.generate(**_kw(feats, fmask, ids, am, ref=True), max_new_tokens=new, do_sample=False, eos_token_id=eos, pad_token_id=0).cpu()
@@ -88,16 +97,18 @@ def test_generate_eos_rows_finish_at_different_steps(O, tiny):
             assert torch.equal(o, _apply_eos_rule(free_our, S, eos, 0)), (eos, graph)
             if same_free:
                 assert torch.equal(o, h)
-    # pad defaults to the first EOS id, as in the reference
-    o = ours.generate(**_kw(feats, fmask, ids, am), max_new_tokens=new, eos_token_id=cands[0]).cpu()
-    assert torch.equal(o, _apply_eos_rule(free_our, S, cands[0], cands[0][0]))
-    # defaults come from the reference model's generation_config when present
+    # defaults: pad_token_id / eos_token_id / max_new_tokens come from generation_config when present; without any,
+    # pad falls back to the first EOS id as in the reference
     saved = ours.generation_config
     try:
         from transformers import GenerationConfig
 
-        ours.generation_config = GenerationConfig(eos_token_id=cands[1], pad_token_id=0, max_new_tokens=new, do_sample=False)
-        assert torch.equal(ours.generate(**_kw(feats, fmask, ids, am)).cpu(), _apply_eos_rule(free_our, S, cands[1], 0))
+        e = cands[0]
+        ours.generation_config = GenerationConfig(eos_token_id=e, pad_token_id=7, max_new_tokens=new, do_sample=False)
+        assert torch.equal(ours.generate(**_kw(feats, fmask, ids, am)).cpu(), _apply_eos_rule(free_our, S, e, 7))
+        ours.generation_config = None
+        o = ours.generate(**_kw(feats, fmask, ids, am), max_new_tokens=new, eos_token_id=e).cpu()
+        assert torch.equal(o, _apply_eos_rule(free_our, S, e, e[0]))
     finally:
         ours.generation_config = saved
 
