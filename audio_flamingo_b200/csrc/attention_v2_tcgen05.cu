@@ -193,7 +193,11 @@ attention2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 #pragma unroll
                 for (int kk = 0; kk < A2_BN / 16; ++kk)
                     umma_bf16_ts(dO, aP + kk * 8, make_smem_desc_sw128(aV + kk * 2048, 16384, 1024), idesc_o, (t | kk) != 0);
-                umma_commit(&o_full[g]);
+                // o_full only announces the LAST product (the epilogue waits for it).  In between, the softmax group knows that
+                // P_g(t-1) V has retired as soon as it has seen s_full for tile t: Q K_t^T was issued after it and tcgen05.mma
+                // retires in issue order.  (Committing o_full every tile completed mbarrier phases nobody waited for, which
+                // compute-sanitizer's synccheck reports as an error.)
+                if (t + 1 == (g ? nB : nA)) umma_commit(&o_full[g]);
             };
             if (nA > 0) qk(0, 0);
             if (nB > 0) qk(1, 0);
@@ -275,9 +279,8 @@ attention2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             if (t > 0) {
                 const bool grow = (m_new - m_ref) > 8.0f;  // also true when m_ref == -inf and m_new finite
                 if (__any_sync(0xffffffffu, grow)) {       // warp-uniform: the TMEM accesses below are .sync.aligned
-                    // O_g is about to be rewritten: P_g(t-1) V must have retired
-                    mbar_wait(&o_full[g], (t - 1) & 1);
-                    tc_fence_after();
+                    // O_g is about to be rewritten: P_g(t-1) V has retired -- S_g(t), whose completion this thread has just
+                    // waited for, was issued after it and tcgen05.mma retires in issue order (see the MMA warp)
                     if (grow) {
                         alpha = (m_ref == -INFINITY) ? 0.f : exp2f(m_ref - m_new);
                         m_ref = m_new;
@@ -340,7 +343,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 
         // ---- epilogue: O / l -> bf16 -> global (one row per thread)
         if (n_g > 0) {
-            mbar_wait(&o_full[g], (n_g - 1) & 1);
+            mbar_wait(&o_full[g], 0);
             tc_fence_after();
         }
         const bool live = (g == 0) || activeB;

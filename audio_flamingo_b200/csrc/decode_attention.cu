@@ -390,13 +390,11 @@ int decode_attention(cudaStream_t stream, const bf16* qkv, const bf16* k_cache, 
     AF3_REQUIRE(ctx_len != nullptr, "decode_attention: ctx_len must be a device pointer");
     AF3_REQUIRE(Hkv <= 65535, "decode_attention: too many KV heads");
     const int nz = pick_splits(B, Hkv, Tmax);
-    // ring depth: 3 stages (192 KB in flight) or 2 (128 KB), the latter so that the kernel can be co-resident with a
-    // few-token GEMM of the decode chain under programmatic dependent launch (AF3_DA_STAGES, experiments)
-    static const int ns = [] { const char* e = getenv("AF3_DA_STAGES"); const int v = e ? atoi(e) : 3; return v == 2 ? 2 : 3; }();
+    // ring depth 3 (192 KB in flight).  A 2-stage ring (so that a few-token GEMM could be co-resident under programmatic dependent
+    // launch) was measured in round 2 and is slower (profiles/r02a_decode_timeline_stages3_3_da2.md).
+    constexpr int ns = 3;
     static DeviceOnce once;
     if (once.first()) {
-        AF3_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, da_smem(2)));
-        AF3_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, da_smem(2)));
         AF3_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_kernel<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, da_smem(3)));
         AF3_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_kernel<16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, da_smem(3)));
     }
@@ -411,8 +409,7 @@ int decode_attention(cudaStream_t stream, const bf16* qkv, const bf16* k_cache, 
         return e;
     dim3 grid(B, Hkv, nz);
     int* counters = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(scratch) + partial_bytes(B, H, D, Tmax));
-    auto kern = (H / Hkv <= 8) ? (ns == 2 ? decode_attn_kernel<8, 2> : decode_attn_kernel<8, 3>)
-                               : (ns == 2 ? decode_attn_kernel<16, 2> : decode_attn_kernel<16, 3>);
+    auto kern = (H / Hkv <= 8) ? decode_attn_kernel<8, 3> : decode_attn_kernel<16, 3>;
     AF3_CHECK_CUDA(launch_kernel(kern, grid, dim3(DA_THREADS), da_smem(ns), stream, mq, mk, mv, scratch, out, counters, H, Hkv, nz,
                                  ctx_len, kv_start, scale * 1.4426950408889634f, trace_next_slot()));
     return 0;

@@ -52,6 +52,19 @@ struct GemmArgs {
     float* ws;      // [tiles][k_splits][BN][128] fp32
     int* counters;  // [tiles], zero on entry, reset to zero by the reducing CTA
     unsigned long long* trace;  // in-graph timeline slot of this launch (common.h) or nullptr
+    // ---- Qwen2RMSNorm fused across two few-token GEMMs of the decode step ([O] Q2M:258-263), removing the norm kernel and its
+    // two dependency hops from the chain (profiles/r02b_decode_timeline.md: 57 x 2.9 us per step):
+    //  * producer (a residual GEMM, transposed epilogue): sumsq_out[row tile][token] = sum over the tile's 128 features of the
+    //    squared bf16 values it just stored;
+    //  * consumer (norm_w != nullptr): rstd[token] = rsqrt(sum over norm_parts partials / K + eps); the epilogue warps -- idle during
+    //    the main loop -- rewrite every activation tile in shared memory as  w[k] * bf16(x[k] * rstd)  (the reference's two roundings)
+    //    between the TMA completion and the MMA issue (mbarrier xf[stage]).  One work item per CTA (checked by the host).
+    const bf16* norm_w;        // [K] RMSNorm weight of the consumer's input norm, or nullptr
+    const float* norm_part;    // [norm_parts][norm_ld] sum-of-squares partials of the input rows
+    int norm_parts, norm_ld;
+    float norm_eps;
+    float* sumsq_out;          // [num_r_tiles][sumsq_ld] or nullptr
+    int sumsq_ld;
 };
 
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle atom row
@@ -66,7 +79,8 @@ struct GemmCfg {
     // normal mode: 4 epilogue warps x 2 buffers x (32 rows x 128 B) staging for the TMA-store epilogue
     // swap mode: one [32 tokens x 128 features] bf16 tile to transpose the accumulator for token-major vector I/O
     static constexpr int EPI_STAGE_BYTES = SWAP ? 32 * 128 * 2 : 4 * 2 * 4096;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers: (3 STAGES + 12) x 8 B + slot*/;
+    static_assert((3 * STAGES + 12) * 8 + 16 <= 512, "barrier area");
     static_assert(2 * ACC_COLS <= 512, "TMEM budget");
     static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
 };
@@ -114,7 +128,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
     uint64_t* tfull = empty + STAGES;
     uint64_t* tempty = tfull + 2;
     uint64_t* rbar = tempty + 2;  // [4 warps][2 buffers] residual-tile arrival
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + 8);
+    uint64_t* xf = rbar + 8;      // [STAGES] activation tile normalised in place (fused RMSNorm, swap mode)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xf + STAGES);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -132,6 +147,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
             mbar_init(&tempty[i], 32 * EW);
         }
         for (int i = 0; i < 8; ++i) mbar_init(&rbar[i], 1);
+        for (int i = 0; i < STAGES; ++i) mbar_init(&xf[i], 32 * EW);
         if (a.tma_epi) {
             tma_prefetch_desc(&map_out);
             if ((((EPI >= 0) ? EPI : a.flags) & EPI_RESID) && a.res_period == 0) tma_prefetch_desc(&map_res);
@@ -216,6 +232,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
                 const int kb0 = kb_lo(sp), kb1 = kb_lo(sp + 1);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full[stage], phase);
+                    if constexpr (SWAP) {
+                        if (a.norm_w) mbar_wait(&xf[stage], phase);  // activation tile rewritten by the epilogue warps (fused RMSNorm)
+                    }
                     tc_fence_after();
                     const uint32_t sR = smem_u32(smem + stage * Cfg::STAGE_BYTES);
                     const uint32_t sC = sR + Cfg::R_BYTES;
@@ -249,6 +268,64 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
         const int flags = (EPI >= 0) ? EPI : a.flags;
         pdl_wait();  // residual reads / output writes / split-K workspace are ordered after every earlier kernel
         if (threadIdx.x == 64) trace_mark(a.trace, 1);
+        if constexpr (SWAP && EW == 4) {
+            if (a.norm_w) {
+                // ---- fused RMSNorm of the activation tiles (this CTA's single work item): thread -> token et / 4, 16-byte chunks
+                //      2 (et % 4), 2 (et % 4) + 1 of the 64-wide k block
+                const int t0 = blockIdx.x;
+                int r0, c0;
+                tile_coords(t0 / k_splits, a, r0, c0);
+                const int sp0 = t0 % k_splits;
+                const int et = threadIdx.x - 64, tt = et >> 2, ch0 = (et & 3) * 2;
+                const int tokg = c0 * BN + tt;
+                float ss = 0.f;
+                if (t0 < num_tiles && tokg < a.n_tok) {
+#pragma unroll 4
+                    for (int p = 0; p < a.norm_parts; ++p) ss += __ldcg(a.norm_part + static_cast<size_t>(p) * a.norm_ld + tokg);
+                }
+                const float rstd = (tokg < a.n_tok) ? rsqrtf(ss / static_cast<float>(a.K) + a.norm_eps) : 0.f;
+                if (t0 < num_tiles) {
+                    int stage = 0;
+                    uint32_t phase = 0;
+                    const int kb0 = kb_lo(sp0), kb1 = kb_lo(sp0 + 1);
+                    const uint4* wv = reinterpret_cast<const uint4*>(a.norm_w);
+                    uint4 w0 = __ldg(wv + kb0 * 8 + ch0), w1 = __ldg(wv + kb0 * 8 + ch0 + 1);
+                    for (int kb = kb0; kb < kb1; ++kb) {
+                        uint4 nw0 = w0, nw1 = w1;
+                        if (kb + 1 < kb1) {   // next k block's norm weights: in flight while this tile is rewritten
+                            nw0 = __ldg(wv + (kb + 1) * 8 + ch0);
+                            nw1 = __ldg(wv + (kb + 1) * 8 + ch0 + 1);
+                        }
+                        mbar_wait(&full[stage], phase);
+                        uint8_t* sX = smem + stage * Cfg::STAGE_BYTES + Cfg::R_BYTES + tt * 128;   // 128B-swizzled [BN][64] bf16 tile
+                        uint4* p0 = reinterpret_cast<uint4*>(sX + ((ch0 ^ (tt & 7)) << 4));
+                        uint4* p1 = reinterpret_cast<uint4*>(sX + (((ch0 + 1) ^ (tt & 7)) << 4));
+                        const uint4 x0 = *p0, x1 = *p1;
+                        auto norm8 = [&](const uint4& xv, const uint4& wq) {
+                            const __nv_bfloat162* xh = reinterpret_cast<const __nv_bfloat162*>(&xv);
+                            const __nv_bfloat162* wh = reinterpret_cast<const __nv_bfloat162*>(&wq);
+                            uint32_t o[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 xf2 = __bfloat1622float2(xh[e]), wf = __bfloat1622float2(wh[e]);
+                                o[e] = pack_bf16x2(wf.x * bf16_round(xf2.x * rstd), wf.y * bf16_round(xf2.y * rstd));
+                            }
+                            return make_uint4(o[0], o[1], o[2], o[3]);
+                        };
+                        *p0 = norm8(x0, w0);
+                        *p1 = norm8(x1, w1);
+                        fence_proxy_async_smem();
+                        mbar_arrive(&xf[stage]);
+                        w0 = nw0;
+                        w1 = nw1;
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
         int acc = 0;
         uint32_t acc_phase = 0;
         uint32_t egrp = 0;             // running 64-column group counter of this warp (selects the staging buffer)
@@ -624,6 +701,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
                             } else if (tok < a.n_tok) {
                                 const uint4* tp = reinterpret_cast<const uint4*>(tile + (et >> 2) * 128 + (et & 3) * 32);
                                 bf16* op = reinterpret_cast<bf16*>(a.out) + static_cast<size_t>(tok) * a.ldo + f0;
+                                float ssq = 0.f;   // sum of squares of the bf16 values stored below (fused RMSNorm producer)
                                 uint4 rv[4];
                                 if (flags & EPI_RESID) {
                                     if constexpr (NA == 1) {
@@ -654,7 +732,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
                                             yv = make_uint4(o4[0], o4[1], o4[2], o4[3]);
                                         }
                                         reinterpret_cast<uint4*>(op)[g4] = yv;
+                                        if (a.sumsq_out) {
+                                            const __nv_bfloat162* yh = reinterpret_cast<const __nv_bfloat162*>(&yv);
+#pragma unroll
+                                            for (int e = 0; e < 4; ++e) {
+                                                const float2 yf = __bfloat1622float2(yh[e]);
+                                                ssq = fmaf(yf.x, yf.x, ssq);
+                                                ssq = fmaf(yf.y, yf.y, ssq);
+                                            }
+                                        }
                                     }
+                                }
+                                if (a.sumsq_out) {
+                                    // the four lanes et % 4 = 0..3 hold the token's 4 x 32 features of this row tile (same warp, same
+                                    // branch: tok is uniform over them); fixed order -> deterministic
+                                    const unsigned grp = 0xFu << (lane & 28);
+                                    ssq += __shfl_xor_sync(grp, ssq, 1);
+                                    ssq += __shfl_xor_sync(grp, ssq, 2);
+                                    if ((et & 3) == 0) a.sumsq_out[static_cast<size_t>(r) * a.sumsq_ld + tok] = ssq;
                                 }
                             }
                             asm volatile("bar.sync 2, 128;" ::: "memory");  // tile may be rewritten by the next work item
@@ -776,9 +871,19 @@ struct RopeEpilogue {
     int H, Hkv, Tmax;
 };
 
+// RMSNorm fusion across few-token GEMMs (see GemmArgs): consumer side (norm_w ...) and / or producer side (sumsq_out ...)
+struct NormFusion {
+    const bf16* norm_w;
+    const float* norm_part;
+    int norm_parts, norm_ld;
+    float norm_eps;
+    float* sumsq_out;
+    int sumsq_ld;
+};
+
 int gemm_bf16(cudaStream_t stream, const bf16* x, int ldx, const bf16* w, int ldw, void* out, int ldo, int n_tok,
               int n_feat, int K, int flags, const bf16* bias, const bf16* resid, int ld_res, int res_period,
-              void* workspace, size_t workspace_bytes, const RopeEpilogue* rope) {
+              void* workspace, size_t workspace_bytes, const RopeEpilogue* rope, const NormFusion* nf) {
     AF3_REQUIRE(n_tok > 0 && n_feat > 0 && K > 0, "gemm: empty problem");
     AF3_REQUIRE((K % 8) == 0 && (ldx % 8) == 0 && (ldw % 8) == 0, "gemm: K and pitches must be multiples of 8");
     AF3_REQUIRE(!(flags & EPI_BIAS) || bias, "gemm: bias flag without pointer");
@@ -798,6 +903,25 @@ int gemm_bf16(cudaStream_t stream, const bf16* x, int ldx, const bf16* w, int ld
     a.flags = flags;
     a.k_splits = 1;
     a.trace = trace_next_slot();
+    if (nf) {
+        AF3_REQUIRE(n_tok <= 64, "gemm: RMSNorm fusion exists for the few-token (decode) GEMMs only");
+        if (nf->norm_w) {
+            AF3_REQUIRE(nf->norm_part && nf->norm_parts > 0 && nf->norm_ld >= n_tok, "gemm: fused RMSNorm needs the sum-of-squares partials");
+            AF3_REQUIRE(K % 64 == 0 && (reinterpret_cast<uintptr_t>(nf->norm_w) & 15) == 0, "gemm: fused RMSNorm needs K % 64 == 0 and a 16-byte aligned weight");
+            a.norm_w = nf->norm_w;
+            a.norm_part = nf->norm_part;
+            a.norm_parts = nf->norm_parts;
+            a.norm_ld = nf->norm_ld;
+            a.norm_eps = nf->norm_eps;
+        }
+        if (nf->sumsq_out) {
+            AF3_REQUIRE(nf->sumsq_ld >= n_tok && !(flags & (EPI_F32OUT | EPI_SWIGLU | EPI_ROPE)) && (ldo % 8) == 0 && res_period == 0 &&
+                            (!(flags & EPI_RESID) || (ld_res % 8) == 0),
+                        "gemm: sum-of-squares output needs the token-major bf16 epilogue");
+            a.sumsq_out = nf->sumsq_out;
+            a.sumsq_ld = nf->sumsq_ld;
+        }
+    }
     if (flags & EPI_ROPE) {
         AF3_REQUIRE(rope && rope->cs && rope->k_cache && rope->v_cache && rope->pos, "gemm: EPI_ROPE needs the rope arguments");
         AF3_REQUIRE(n_tok <= 64 && n_feat == (rope->H + 2 * rope->Hkv) * 128 && (ldo % 8) == 0 && !(flags & (EPI_RESID | EPI_F32OUT | EPI_SWIGLU)),
@@ -847,17 +971,13 @@ int gemm_bf16(cudaStream_t stream, const bf16* x, int ldx, const bf16* w, int ld
     a.group_r = 1;
     if (int e = make_tmap_2d(&mw, w, K, w_rows, ldw, BK, 128)) return e;
     if (int e = make_tmap_2d(&mx, x, K, n_tok, ldx, BK, BN)) return e;
-    // Few-token pipeline depth.  Under programmatic dependent launch the NEXT kernel of the decode chain can only become
-    // resident (and start its pre-wait weight prefetch) while this one still runs if both fit in one SM's 227 KB of
-    // shared memory: 4 x 20 KB (NA = 1) / 3 x 36 KB (NA = 2) stages keep 64 / 96 KB of weights in flight per SM -- above
-    // the ~45 KB that HBM latency x per-SM bandwidth needs -- and leave room for the successor.  AF3_SWAP_STAGES /
-    // AF3_SWAP_STAGES2 select the depth (experiments; the defaults are the measured optimum).
-    static const int st1 = [] { const char* e = getenv("AF3_SWAP_STAGES"); return e ? atoi(e) : 8; }();
-    static const int st2 = [] { const char* e = getenv("AF3_SWAP_STAGES2"); return e ? atoi(e) : 6; }();
+    // Pipeline depth of the few-token mode: 8 x 20 KB (NA = 1) / 6 x 36 KB (NA = 2) stages.  Shallower rings (4 / 3 stages, so that
+    // the NEXT kernel of the decode chain could be co-resident and prefetch under programmatic dependent launch) were measured
+    // in round 2 and are slower: a single SM pulls at most ~58 GB/s from HBM (profiles/r02b_microbench_splitk.json), the streams
+    // need the deep ring, and the co-resident successor does not shorten the dependent tails (profiles/r02a_decode_timeline_*.md).
     if (swiglu) {
         a.num_r_tiles = ceil_div(w_rows, 256);
-        if (st2 == 3 && flags == EPI_SWIGLU) return launch_epi<BN, 2, 3, true, EPI_SWIGLU>(mw, mx, mw, mw, a, stream);
-        if (st2 == 4 && flags == EPI_SWIGLU) return launch_epi<BN, 2, 4, true, EPI_SWIGLU>(mw, mx, mw, mw, a, stream);
+        AF3_REQUIRE(!a.norm_w || a.num_r_tiles * a.num_c_tiles <= sm_count(), "gemm: fused RMSNorm needs one work item per CTA");
         return launch<BN, 2, 6, true>(mw, mx, mw, mw, a, stream);
     }
     a.num_r_tiles = ceil_div(w_rows, 128);
@@ -877,17 +997,7 @@ int gemm_bf16(cudaStream_t stream, const bf16* x, int ldx, const bf16* w, int ld
             a.counters = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(workspace) + (8u << 20));
         }
     }
-#define AF3_SWAP1_CASE(ST)                                                                                          \
-    if (st1 == ST) {                                                                                                \
-        if (flags == EPI_RESID) return launch_epi<BN, 1, ST, true, EPI_RESID>(mw, mx, mw, mw, a, stream);           \
-        if (flags == (EPI_BIAS | EPI_ROPE)) return launch_epi<BN, 1, ST, true, EPI_BIAS | EPI_ROPE>(mw, mx, mw, mw, a, stream); \
-        if (flags == EPI_F32OUT) return launch_epi<BN, 1, ST, true, EPI_F32OUT>(mw, mx, mw, mw, a, stream);         \
-    }
-    AF3_SWAP1_CASE(3)
-    AF3_SWAP1_CASE(4)
-    AF3_SWAP1_CASE(5)
-    AF3_SWAP1_CASE(6)
-#undef AF3_SWAP1_CASE
+    AF3_REQUIRE(!a.norm_w || a.num_r_tiles * a.num_c_tiles * a.k_splits <= sm_count(), "gemm: fused RMSNorm needs one work item per CTA");
     return launch<BN, 1, 8, true>(mw, mx, mw, mw, a, stream);
 }
 

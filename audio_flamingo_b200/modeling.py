@@ -340,35 +340,56 @@ class Qwen2ForCausalLM(nn.Module):
         pos0 = cache.length
         rope_cs = None
         fused_qkv = decode and B <= 64  # few-token ("swapped") GEMM with RoPE + KV append in its epilogue
+        # Decode step: RMSNorm fused ACROSS the GEMMs (include/af3b200.h af3_gemm_fusion).  The residual GEMMs (o, down) emit the
+        # per-row-tile sums of squares of the rows they store; the next q/k/v / gate-up GEMM normalises its activation tiles in
+        # shared memory.  55 of the 57 norm launches of a step (and two dependency hops each) disappear; only layer 0's input
+        # norm (input from the embedding gather) and the final norm stay kernels.  AF3_FUSE_NORM=0: the round-1 chain (A/B runs).
+        fuse_norm = fused_qkv and self.hid % 64 == 0 and os.environ.get("AF3_FUSE_NORM", "1") != "0"
         if fused_qkv:
             rope_cs = ops.rope_table(B, D, cache.pos_dev, cache.kv_start, self._inv_freq)
+        ss = ss_attn = ss_mlp = None   # ss: partials describing the CURRENT residual stream h (None -> stand-alone norm kernel)
+        if fuse_norm:
+            ss_attn, ss_mlp = ops.sumsq_buffer(self.hid, B, h.device), ops.sumsq_buffer(self.hid, B, h.device)
+        y = None
         for li, (l, (wqkv, bqkv, wgu)) in enumerate(zip(self.model.layers, self._packed)):
-            y = ops.rmsnorm(h, l.input_layernorm.weight, self.eps)
             kc, vc = cache.k[li], cache.v[li]
             a = torch.empty((B * T, H * D), device=h.device, dtype=bf16)
             if decode:
                 if fused_qkv:
                     # q/k/v projection with RoPE + KV append in the GEMM epilogue (rope table: once per step, above)
-                    qkv = ops.qkv_rope_linear(y, wqkv, bqkv, kc, vc, H=H, Hkv=Hkv, D=D, rope_cs=rope_cs, pos_dev=cache.pos_dev)
+                    if ss is not None:
+                        qkv = ops.qkv_rope_linear(h, wqkv, bqkv, kc, vc, H=H, Hkv=Hkv, D=D, rope_cs=rope_cs, pos_dev=cache.pos_dev,
+                                                  norm=(l.input_layernorm.weight, ss, self.eps))
+                    else:
+                        y = ops.rmsnorm(h, l.input_layernorm.weight, self.eps, out=y)
+                        qkv = ops.qkv_rope_linear(y, wqkv, bqkv, kc, vc, H=H, Hkv=Hkv, D=D, rope_cs=rope_cs, pos_dev=cache.pos_dev)
                 else:
                     # more than 64 sequences per GPU: token-major tensor-core GEMM + the stand-alone RoPE / append kernel reading
                     # the slot from device memory (graph replay)
+                    y = ops.rmsnorm(h, l.input_layernorm.weight, self.eps, out=y)
                     qkv = ops.linear(y, wqkv, bqkv)
                     ops.rope_kv_append(qkv, kc, vc, B=B, T=1, H=H, Hkv=Hkv, D=D, pos0=0, inv_freq=self._inv_freq,
                                        kv_start=cache.kv_start, pos0_dev=cache.pos_dev)
                 ops.decode_attention(qkv, kc, vc, a, scratch, B=B, H=H, Hkv=Hkv, D=D, ctx_len=cache.ctx_dev,
                                      kv_start=cache.kv_start, scale=D ** -0.5)
             else:
+                y = ops.rmsnorm(h, l.input_layernorm.weight, self.eps, out=y)
                 qkv = ops.linear(y, wqkv, bqkv)
                 ops.rope_kv_append(qkv, kc, vc, B=B, T=T, H=H, Hkv=Hkv, D=D, pos0=pos0, inv_freq=self._inv_freq,
                                    kv_start=cache.kv_start)
                 ops.attention(qkv, kc, vc, a.view(B, T, H * D), B=B, H=H, Hkv=Hkv, D=D, Tq=T, Tk=pos0 + T, scale=D ** -0.5,
                               causal=True, kv_layout=1, Tk_pitch=cache.Tmax, ldq=(H + 2 * Hkv) * D, ldk=D,
                               kv_start=cache.kv_start)
-            ops.linear(a, l.self_attn.o_proj.weight, resid=h, out=h)
-            y = ops.rmsnorm(h, l.post_attention_layernorm.weight, self.eps, out=y)
-            g = ops.swiglu_linear(y, wgu, self.inter)
-            ops.linear(g, l.mlp.down_proj.weight, resid=h, out=h)
+            if fuse_norm:
+                ops.linear(a, l.self_attn.o_proj.weight, resid=h, out=h, sumsq_out=ss_attn)
+                g = ops.swiglu_linear(h, wgu, self.inter, norm=(l.post_attention_layernorm.weight, ss_attn, self.eps))
+                ops.linear(g, l.mlp.down_proj.weight, resid=h, out=h, sumsq_out=ss_mlp)
+                ss = ss_mlp
+            else:
+                ops.linear(a, l.self_attn.o_proj.weight, resid=h, out=h)
+                y = ops.rmsnorm(h, l.post_attention_layernorm.weight, self.eps, out=y)
+                g = ops.swiglu_linear(y, wgu, self.inter)
+                ops.linear(g, l.mlp.down_proj.weight, resid=h, out=h)
         return h
 
     def _head(self, h, row_idx=None):
@@ -709,7 +730,7 @@ class AudioFlamingo3ForConditionalGeneration(nn.Module):
             Tmax = AF3KVCache.bucket(S + max_new_tokens)
             # the captured graph holds raw addresses: key it on the weight storages too, so a re-pack (load_reference_state_dict) or
             # a move (.to()) can never leave a stale graph replaying against freed memory
-            key = (B, Tmax, use_graph, os.environ.get("AF3_PDL", "1") != "0", str(dev),
+            key = (B, Tmax, use_graph, os.environ.get("AF3_PDL", "1") != "0", os.environ.get("AF3_FUSE_NORM", "1") != "0", str(dev),
                    lm.lm_head.weight.data_ptr(), lm._packed[0][0].data_ptr(), lm._packed[-1][2].data_ptr())
             st = self._decode_state
             if st is not None and st["key"] == key:

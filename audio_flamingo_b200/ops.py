@@ -5,6 +5,7 @@ through ctypes.  All arithmetic happens in libaf3b200.so; nothing here falls bac
 """
 from __future__ import annotations
 
+import ctypes as C
 import math
 
 import numpy as np
@@ -80,8 +81,29 @@ def gemm_workspace(device):
     return ws
 
 
-def linear(x, w, bias=None, *, gelu=False, resid=None, res_period=0, out=None, out_f32=False):
-    """out = epi(x @ w.T); x [n_tok, K] bf16, w [n_feat, K] bf16 (nn.Linear layout)."""
+def _fusion(norm, sumsq_out):
+    """ctypes af3_gemm_fusion or None.  norm = (weight bf16 [K], partials fp32 [parts, ld], eps); sumsq_out fp32 [row tiles, ld]."""
+    if norm is None and sumsq_out is None:
+        return None
+    f = _lib.GemmFusion()
+    if norm is not None:
+        wn, part, eps = norm
+        _req(wn, bf16, "norm weight"), _req(part, torch.float32, "norm partials")
+        f.norm_weight, f.norm_sumsq, f.norm_parts, f.norm_ld, f.norm_eps = ptr(wn), ptr(part), part.shape[0], part.stride(0), float(eps)
+    if sumsq_out is not None:
+        _req(sumsq_out, torch.float32, "sumsq_out")
+        f.sumsq_out, f.sumsq_ld = ptr(sumsq_out), sumsq_out.stride(0)
+    return f
+
+
+def sumsq_buffer(n_feat, n_tok, device):
+    """fp32 [ceil(n_feat / 128), n_tok]: per-row-tile sums of squares a residual GEMM emits for the next fused RMSNorm."""
+    return torch.empty(((n_feat + 127) // 128, n_tok), device=device, dtype=torch.float32)
+
+
+def linear(x, w, bias=None, *, gelu=False, resid=None, res_period=0, out=None, out_f32=False, norm=None, sumsq_out=None):
+    """out = epi(x @ w.T); x [n_tok, K] bf16, w [n_feat, K] bf16 (nn.Linear layout).
+    norm / sumsq_out: RMSNorm fusion across few-token GEMMs (include/af3b200.h af3_gemm_fusion)."""
     lib = _lib.load()
     _req(x, bf16, "x"), _req(w, bf16, "w")
     n_tok, K = x.shape
@@ -100,11 +122,12 @@ def linear(x, w, bias=None, *, gelu=False, resid=None, res_period=0, out=None, o
     if out is None:
         out = torch.empty((n_tok, n_feat), device=x.device, dtype=torch.float32 if out_f32 else bf16)
     ws = gemm_workspace(x.device) if n_tok <= 64 else None
+    fus = _fusion(norm, sumsq_out)
     with _Timed(("gemm", n_tok, n_feat, K, flags)):
         check(
-            lib.af3_gemm_bf16_ws(stream_ptr(), ptr(x), x.stride(0), ptr(w), w.stride(0), ptr(out), out.stride(0), n_tok, n_feat,
-                                 K, flags, ptr(bias), ptr(resid), resid.stride(0) if resid is not None else 0, res_period,
-                                 ptr(ws), ws.numel() if ws is not None else 0),
+            lib.af3_gemm_bf16_fused(stream_ptr(), ptr(x), x.stride(0), ptr(w), w.stride(0), ptr(out), out.stride(0), n_tok, n_feat,
+                                    K, flags, ptr(bias), ptr(resid), resid.stride(0) if resid is not None else 0, res_period,
+                                    ptr(ws), ws.numel() if ws is not None else 0, C.byref(fus) if fus is not None else None),
             "af3_gemm_bf16",
         )
     _count(1)
@@ -121,17 +144,18 @@ def pack_gate_up(gate, up):
     return packed
 
 
-def swiglu_linear(x, w_packed, n_feat, out=None):
-    """out = silu(x @ gate.T) * (x @ up.T) with w_packed from pack_gate_up."""
+def swiglu_linear(x, w_packed, n_feat, out=None, norm=None):
+    """out = silu(x @ gate.T) * (x @ up.T) with w_packed from pack_gate_up; norm: fused RMSNorm of x (few-token mode)."""
     lib = _lib.load()
     _req(x, bf16, "x"), _req(w_packed, bf16, "w_packed")
     n_tok, K = x.shape
     if out is None:
         out = torch.empty((n_tok, n_feat), device=x.device, dtype=bf16)
+    fus = _fusion(norm, None)
     with _Timed(("gemm", n_tok, n_feat, K, EPI_SWIGLU)):
         check(
-            lib.af3_gemm_bf16(stream_ptr(), ptr(x), x.stride(0), ptr(w_packed), w_packed.stride(0), ptr(out), out.stride(0),
-                              n_tok, n_feat, K, EPI_SWIGLU, None, None, 0, 0),
+            lib.af3_gemm_bf16_fused(stream_ptr(), ptr(x), x.stride(0), ptr(w_packed), w_packed.stride(0), ptr(out), out.stride(0),
+                                    n_tok, n_feat, K, EPI_SWIGLU, None, None, 0, 0, None, 0, C.byref(fus) if fus is not None else None),
             "af3_gemm_bf16(swiglu)",
         )
     _count(1)
@@ -289,7 +313,7 @@ def rope_table(B, D, pos_dev, kv_start, inv_freq, out=None):
     return out
 
 
-def qkv_rope_linear(x, w, bias, k_cache, v_cache, *, H, Hkv, D, rope_cs, pos_dev, out=None):
+def qkv_rope_linear(x, w, bias, k_cache, v_cache, *, H, Hkv, D, rope_cs, pos_dev, out=None, norm=None):
     """Decode-step q/k/v projection with RoPE + KV append fused into the GEMM epilogue.  Returns the [n_tok, (H+2Hkv)*D]
     buffer whose first H*D columns hold the rotated queries (k / v go straight into the caches)."""
     lib = _lib.load()
@@ -299,10 +323,12 @@ def qkv_rope_linear(x, w, bias, k_cache, v_cache, *, H, Hkv, D, rope_cs, pos_dev
         out = torch.empty((n_tok, (H + 2 * Hkv) * D), device=x.device, dtype=bf16)
     ws = gemm_workspace(x.device)
     Tmax = k_cache.shape[2]
+    fus = _fusion(norm, None)
     with _Timed(("gemm", n_tok, (H + 2 * Hkv) * D, K, EPI_BIAS | 32)):
         check(
             lib.af3_gemm_qkv_rope(stream_ptr(), ptr(x), x.stride(0), ptr(w), w.stride(0), ptr(bias), ptr(out), out.stride(0), n_tok, K,
-                                  H, Hkv, D, ptr(rope_cs), ptr(k_cache), ptr(v_cache), Tmax, ptr(pos_dev), ptr(ws), ws.numel()),
+                                  H, Hkv, D, ptr(rope_cs), ptr(k_cache), ptr(v_cache), Tmax, ptr(pos_dev), ptr(ws), ws.numel(),
+                                  C.byref(fus) if fus is not None else None),
             "af3_gemm_qkv_rope",
         )
     _count(1)

@@ -128,9 +128,33 @@ int af3_rotary_time_emb(void* stream, void* x, const float* timestamps, const fl
  * n_tok <= 64, D = 128, bias required (Qwen2 q/k/v have biases). */
 int af3_rope_table(void* stream, float* rope_cs, int B, int D, const int* pos_dev, const int* kv_start,
                    const float* inv_freq);
+
+/* Qwen2RMSNorm ([O] Q2M:258-263) fused ACROSS two few-token (n_tok <= 64) GEMMs of the decode step, so that the norm kernel and
+ * its two dependency hops leave the step's kernel chain (profiles/r02b_decode_timeline.md: 57 norm launches x 2.9 us per step):
+ *   producer side (a GEMM with the bf16 token-major epilogue, typically the residual o / down projection): sumsq_out
+ *     [ceil(n_feat / 128)][sumsq_ld] receives, per 128-feature row tile and token, the sum of squares of the bf16 values the
+ *     GEMM stored;
+ *   consumer side (the next q/k/v or gate/up projection): x is the UN-normalised residual stream; with norm_weight [K] bf16 and the
+ *     producer's partials (norm_sumsq [norm_parts][norm_ld]) the kernel computes rstd = rsqrt(sum / K + eps) per token and feeds
+ *     the tensor cores  norm_weight[k] * bf16(x[k] * rstd)  -- the reference's two roundings -- instead of x.
+ * Either side may be left out (NULL pointers).  K % 64 == 0; the consumer must fit one work item per SM (true for the decode
+ * shapes; checked).  Deterministic (fixed summation order). */
+typedef struct af3_gemm_fusion {
+    const void* norm_weight; /* bf16 [K] or NULL */
+    const float* norm_sumsq; /* [norm_parts][norm_ld] */
+    int norm_parts, norm_ld;
+    float norm_eps;
+    float* sumsq_out;        /* [ceil(n_feat/128)][sumsq_ld] or NULL */
+    int sumsq_ld;
+} af3_gemm_fusion;
+/* af3_gemm_bf16_ws plus the fusion descriptor (NULL = plain). */
+int af3_gemm_bf16_fused(void* stream, const void* x, int ldx, const void* w, int ldw, void* out, int ldo, int n_tok,
+                        int n_feat, int K, int flags, const void* bias, const void* resid, int ld_res, int res_period,
+                        void* workspace, size_t workspace_bytes, const af3_gemm_fusion* fusion);
+
 int af3_gemm_qkv_rope(void* stream, const void* x, int ldx, const void* w, int ldw, const void* bias, void* q_out, int ldo,
                       int n_tok, int K, int H, int Hkv, int D, const float* rope_cs, void* k_cache, void* v_cache, int Tmax,
-                      const int* pos_dev, void* workspace, size_t workspace_bytes);
+                      const int* pos_dev, void* workspace, size_t workspace_bytes, const af3_gemm_fusion* fusion /* consumer side or NULL */);
 
 /* Single-token attention over the KV cache (decode step; SDPA:40-104 with q_len = 1).  ctx_len is read from device
  * memory so the launch can live in a CUDA graph.  q at qkv (packed [B, (H+2Hkv)*D]); out [B, H*D].

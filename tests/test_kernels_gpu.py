@@ -436,3 +436,37 @@ def test_attention_v2_matches_v1_on_a_live_cache_offset(ops, monkeypatch):
     _close(outs["0"], ref, 2e-2, 2e-2, "v2 vs fp32")
     _close(outs["1"], ref, 2e-2, 2e-2, "v1 vs fp32")
     _close(outs["0"], outs["1"], 2 ** -6, 2e-3, "v2 vs v1")
+
+
+@pytest.mark.parametrize("B,K,N,mode", [(32, 3584, 4608, "plain"), (7, 3584, 3584, "plain"), (32, 3584, 18944, "swiglu"), (32, 256, 384, "swiglu"),
+                                        (48, 512, 256, "plain")])
+def test_fused_rmsnorm_across_few_token_gemms(ops, B, K, N, mode):
+    """Decode-step fusion (af3_gemm_fusion): a residual GEMM emits per-row-tile sums of squares of what it stores; the next GEMM
+    normalises its activation tiles in shared memory.  Producer: partials == torch's sums over each 128-feature tile of the stored
+    bf16 values.  Consumer: GEMM(x, norm=...) vs GEMM(rmsnorm_kernel(x)): identical up to the last fp32 bit of rstd, i.e. at most one
+    bf16 ulp on a vanishing share of the activations -> outputs within bf16 rounding of each other."""
+    F = K                                  # the producer's output features are the consumer's K
+    a, wo, res = _rand((B, 640), 1.0, 80), _rand((F, 640), 0.05, 81), _rand((B, F), 1.0, 82)
+    ss = ops.sumsq_buffer(F, B, "cuda")
+    h = ops.linear(a, wo, resid=res.clone(), sumsq_out=ss)
+    h_plain = ops.linear(a, wo, resid=res.clone())
+    assert torch.equal(h, h_plain)
+    ref_ss = h.float().pow(2).view(B, -1, 128).sum(-1).T if F % 128 == 0 else None
+    if ref_ss is not None:
+        assert torch.allclose(ss, ref_ss, rtol=1e-5, atol=1e-6), (ss - ref_ss).abs().max().item()
+    wn = _rand((K,), 0.3, 83) + 1.0
+    wn = wn.to(bf16)
+    y = ops.rmsnorm(h, wn, 1e-6)
+    if mode == "swiglu":
+        g, u = _rand((N, K), 0.05, 84), _rand((N, K), 0.05, 85)
+        wp = ops.pack_gate_up(g, u)
+        unf = ops.swiglu_linear(y, wp, N)
+        fus = ops.swiglu_linear(h, wp, N, norm=(wn, ss, 1e-6))
+    else:
+        w2, b2 = _rand((N, K), 0.05, 86), _rand((N,), 0.3, 87)
+        unf = ops.linear(y, w2, b2)
+        fus = ops.linear(h, w2, b2, norm=(wn, ss, 1e-6))
+    d = (fus.float() - unf.float()).abs()
+    tol = 2 ** -7 * unf.float().abs() + 2e-2
+    assert int((d > tol).sum()) == 0, f"max diff {d.max().item()}"
+    assert (d > 0).float().mean().item() < 0.05, "fused and unfused should agree bit for bit almost everywhere"
