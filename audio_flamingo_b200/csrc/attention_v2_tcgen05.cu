@@ -242,7 +242,9 @@ attention2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             float m_tile;
             {
                 float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
+                // not unrolled over the column chunks: the fully unrolled kernel was 64 KB of SASS and the softmax warps spent 19 %
+                // of their non-waiting samples on instruction-cache misses (stall_no_inst, profiles/r02c_ncu_attention_v2.md)
+#pragma unroll 1
                 for (int c = 0; c < 4; c += 2) {
                     uint32_t v0[32], v1[32];
                     tmem_ld32(s_col + c * 32, v0);
@@ -305,7 +307,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
             auto pass2 = [&](auto masked_tag) {
                 constexpr bool MASKED = decltype(masked_tag)::value;
-#pragma unroll
+#pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
                     uint32_t v[32];
                     tmem_ld32(s_col + c * 32, v);

@@ -49,21 +49,26 @@ struct GemmArgs {
     int rope_H, rope_Hkv, rope_Tmax;
     int tma_epi;    // normal mode: stage the output tile in smem and write it with TMA (coalesced); residual via TMA too
     int k_splits;
+    // cluster_reduce: the k_splits CTAs of a tile form a thread-block cluster and exchange their fp32 partial tiles through
+    // distributed shared memory: CTA q of the cluster receives everyone's partials for ITS slice of the 32 tokens, sums them in
+    // split order (deterministic) and runs the fused epilogue for that slice.  No global workspace, no fences, no atomics, no
+    // L2 round trips in the tail (round 2: the split-K tails were the largest loss of the decode step).
+    int cluster_reduce;
     float* ws;      // [tiles][k_splits][BN][128] fp32
     int* counters;  // [tiles], zero on entry, reset to zero by the reducing CTA
     unsigned long long* trace;  // in-graph timeline slot of this launch (common.h) or nullptr
     // ---- Qwen2RMSNorm fused across two few-token GEMMs of the decode step ([O] Q2M:258-263), removing the norm kernel and its
     // two dependency hops from the chain (profiles/r02b_decode_timeline.md: 57 x 2.9 us per step):
-    //  * producer (a residual GEMM, transposed epilogue): sumsq_out[row tile][token] = sum over the tile's 128 features of the
+    //  * producer (a residual GEMM, transposed epilogue): sumsq_out[token][row tile] = sum over the tile's 128 features of the
     //    squared bf16 values it just stored;
     //  * consumer (norm_w != nullptr): rstd[token] = rsqrt(sum over norm_parts partials / K + eps); the epilogue warps -- idle during
     //    the main loop -- rewrite every activation tile in shared memory as  w[k] * bf16(x[k] * rstd)  (the reference's two roundings)
     //    between the TMA completion and the MMA issue (mbarrier xf[stage]).  One work item per CTA (checked by the host).
     const bf16* norm_w;        // [K] RMSNorm weight of the consumer's input norm, or nullptr
-    const float* norm_part;    // [norm_parts][norm_ld] sum-of-squares partials of the input rows
+    const float* norm_part;    // [n_tok][norm_ld] sum-of-squares partials of the input rows, norm_parts (<= 32) used per row
     int norm_parts, norm_ld;
     float norm_eps;
-    float* sumsq_out;          // [num_r_tiles][sumsq_ld] or nullptr
+    float* sumsq_out;          // [n_tok][sumsq_ld], entry [tok][row tile], or nullptr
     int sumsq_ld;
 };
 
@@ -78,7 +83,10 @@ struct GemmCfg {
     static constexpr int TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128) ? 128 : (2 * ACC_COLS <= 256) ? 256 : 512;
     // normal mode: 4 epilogue warps x 2 buffers x (32 rows x 128 B) staging for the TMA-store epilogue
     // swap mode: one [32 tokens x 128 features] bf16 tile to transpose the accumulator for token-major vector I/O
-    static constexpr int EPI_STAGE_BYTES = SWAP ? 32 * 128 * 2 : 4 * 2 * 4096;
+    // + (few-token, NA = 1) the landing zone of the cluster split-K reduction: [k_splits][ceil(32 / k_splits)][128] fp32 partial
+    //   slices written by the peer CTAs through distributed shared memory (<= 18.5 KB for 2..8 splits)
+    static constexpr int ZONE_BYTES = (SWAP && NA == 1) ? 19456 : 0;
+    static constexpr int EPI_STAGE_BYTES = (SWAP ? 32 * 128 * 2 : 4 * 2 * 4096) + ZONE_BYTES;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers: (3 STAGES + 12) x 8 B + slot*/;
     static_assert((3 * STAGES + 12) * 8 + 16 <= 512, "barrier area");
     static_assert(2 * ACC_COLS <= 512, "TMEM budget");
@@ -163,6 +171,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_launch_dependents();  // the next kernel may start its prologue / weight prefetch behind us
+    if constexpr (SWAP && NA == 1) {
+        // cluster split-K: phase 1 of the cluster barrier only says "this CTA is running" (a peer's shared memory may be written
+        // once it is); everybody arrives here without blocking and waits right before its first remote store / at its end
+        if (a.cluster_reduce) cluster_arrive_relaxed();
+    }
 
     const int k_splits = SWAP ? a.k_splits : 1;
     const int num_tiles = a.num_r_tiles * a.num_c_tiles * k_splits;  // work items: (tile, split), split fastest
@@ -217,6 +230,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
             }
         }
         __syncwarp();
+        if constexpr (SWAP && NA == 1) {
+            if (a.cluster_reduce) {   // every thread of the cluster takes part in both phases of the cluster barrier
+                cluster_wait_acquire();
+                cluster_arrive_release();
+                cluster_wait_acquire();
+            }
+        }
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
@@ -261,6 +281,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
             }
         }
         __syncwarp();
+        if constexpr (SWAP && NA == 1) {
+            if (a.cluster_reduce) {
+                cluster_wait_acquire();
+                cluster_arrive_release();
+                cluster_wait_acquire();
+            }
+        }
     } else {
         const int q = warp & 3;  // TMEM lane quarter this warp may access
         [[maybe_unused]] const int ehalf = (EW == 8) ? ((warp - 2) >> 2) : 0;  // which half of the column groups (EW == 8)
@@ -280,8 +307,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
                 const int tokg = c0 * BN + tt;
                 float ss = 0.f;
                 if (t0 < num_tiles && tokg < a.n_tok) {
-#pragma unroll 4
-                    for (int p = 0; p < a.norm_parts; ++p) ss += __ldcg(a.norm_part + static_cast<size_t>(p) * a.norm_ld + tokg);
+                    // all partials of the token in ONE round trip: 8 independent 16-byte loads (<= 32 partials, zero padded by
+                    // the count test), then a fixed-order sum.  (A loop of dependent scalar loads cost 7 L2 round trips = 5 us per
+                    // launch in the first version, profiles/r02d_decode_timeline_fused_norm_v1.md.)
+                    const float4* pp = reinterpret_cast<const float4*>(a.norm_part + static_cast<size_t>(tokg) * a.norm_ld);
+                    float4 pv[8];
+#pragma unroll
+                    for (int q4 = 0; q4 < 8; ++q4) pv[q4] = (q4 * 4 < a.norm_parts) ? __ldcg(pp + q4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int q4 = 0; q4 < 8; ++q4) {
+                        const int p0 = q4 * 4;
+                        ss += (p0 < a.norm_parts) ? pv[q4].x : 0.f;
+                        ss += (p0 + 1 < a.norm_parts) ? pv[q4].y : 0.f;
+                        ss += (p0 + 2 < a.norm_parts) ? pv[q4].z : 0.f;
+                        ss += (p0 + 3 < a.norm_parts) ? pv[q4].w : 0.f;
+                    }
                 }
                 const float rstd = (tokg < a.n_tok) ? rsqrtf(ss / static_cast<float>(a.K) + a.norm_eps) : 0.f;
                 if (t0 < num_tiles) {
@@ -589,8 +629,37 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
                     tmem_ld32(taddr + ch * 32, v);
                     if constexpr (NA == 2) tmem_ld32(taddr + BN + ch * 32, u);
                     tmem_ld_wait();
+                    [[maybe_unused]] int tok_lo = 0, tok_hi = 0x7fffffff;   // tokens this CTA finishes (cluster reduce: its slice)
                     if constexpr (NA == 1 && BN == 32) {
-                        if (k_splits > 1) {
+                        if (k_splits > 1 && a.cluster_reduce) {
+                            const int ks = k_splits, rank = t % k_splits;       // == %cluster_ctarank (consecutive CTAs form a cluster)
+                            const int tokmax = (32 + ks - 1) / ks;
+                            float* zone = reinterpret_cast<float*>(epi_stage + 32 * 128 * 2);   // [ks][tokmax][128]
+                            const uint32_t zone_cta = smem_u32(zone);
+                            cluster_wait_acquire();   // phase 1: every CTA of the cluster is running
+                            // rank q owns tokens [q * 32 / ks, (q + 1) * 32 / ks): send it this CTA's partials of those tokens
+#pragma unroll 1
+                            for (int q = 0; q < ks; ++q) {
+                                const int lo_q = (q * 32) / ks, hi_q = ((q + 1) * 32) / ks;
+                                const uint32_t dst = mapa_shared(zone_cta, q) + (((rank * tokmax - lo_q) * 128 + row_in_tile) << 2);
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    if (j >= lo_q && j < hi_q) st_cluster_f32(dst + j * 512, __uint_as_float(v[j]));
+                            }
+                            cluster_arrive_release();
+                            cluster_wait_acquire();
+                            const int lo = (rank * 32) / ks, hi = ((rank + 1) * 32) / ks;
+                            tok_lo = c * BN + lo;
+                            tok_hi = c * BN + hi;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                if (j >= lo && j < hi) {
+                                    float sum = 0.f;
+                                    for (int s2 = 0; s2 < ks; ++s2) sum += zone[(s2 * tokmax + (j - lo)) * 128 + row_in_tile];   // split order
+                                    v[j] = __float_as_uint(sum);
+                                }
+                            }
+                        } else if (k_splits > 1) {
                             // publish this split's partial tile: ws[tile][split][col][row] (row fastest: coalesced)
                             const int tile = t / k_splits, sp = t % k_splits;
                             float* wt = a.ws + (static_cast<size_t>(tile) * k_splits) * (BN * 128);
@@ -656,7 +725,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
                             const int et = threadIdx.x - 64;             // 0..127 within the epilogue warps
                             const int tok = tok0 + (et >> 2);
                             const int f0 = r * 128 + (et & 3) * 32;      // first of this thread's 32 features
-                            if ((flags & EPI_ROPE) && tok < a.n_tok) {
+                            const bool mine = tok >= tok_lo && tok < tok_hi;
+                            if ((flags & EPI_ROPE) && tok < a.n_tok && mine) {
                                 // tile r = head r of the fused projection: [0,H) query, [H,H+Hkv) key, then value heads
                                 const int head = r, q4 = et & 3;
                                 const uint4* tp = reinterpret_cast<const uint4*>(tile + (et >> 2) * 128 + q4 * 32);
@@ -698,7 +768,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
 #pragma unroll
                                     for (int g4 = 0; g4 < 4; ++g4) reinterpret_cast<uint4*>(op)[g4] = tp[g4];
                                 }
-                            } else if (tok < a.n_tok) {
+                            } else if (!(flags & EPI_ROPE) && tok < a.n_tok && mine) {
                                 const uint4* tp = reinterpret_cast<const uint4*>(tile + (et >> 2) * 128 + (et & 3) * 32);
                                 bf16* op = reinterpret_cast<bf16*>(a.out) + static_cast<size_t>(tok) * a.ldo + f0;
                                 float ssq = 0.f;   // sum of squares of the bf16 values stored below (fused RMSNorm producer)
@@ -749,7 +819,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
                                     const unsigned grp = 0xFu << (lane & 28);
                                     ssq += __shfl_xor_sync(grp, ssq, 1);
                                     ssq += __shfl_xor_sync(grp, ssq, 2);
-                                    if ((et & 3) == 0) a.sumsq_out[static_cast<size_t>(r) * a.sumsq_ld + tok] = ssq;
+                                    if ((et & 3) == 0) a.sumsq_out[static_cast<size_t>(tok) * a.sumsq_ld + r] = ssq;
                                 }
                             }
                             asm volatile("bar.sync 2, 128;" ::: "memory");  // tile may be rewritten by the next work item
@@ -809,6 +879,41 @@ static int launch_epi(const CUtensorMap& mr, const CUtensorMap& mc, const CUtens
     static DeviceOnce once;
     if (once.first()) {
         AF3_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    }
+    if constexpr (SWAP && NA == 1) {
+        if (a.cluster_reduce && a.k_splits > 1) {
+            // cluster split-K: the largest split count <= the requested one for which all tiles' clusters are co-resident
+            // (a cluster needs k_splits free SMs inside ONE GPC; the answer is cached per device and cluster size)
+            static int cache[128][9];
+            static bool cache_init = false;
+            if (!cache_init) {
+                for (auto& row : cache)
+                    for (int& v : row) v = -1;
+                cache_init = true;
+            }
+            const int dev = current_device() & 127;
+            const int base_tiles = a.num_r_tiles * a.num_c_tiles;
+            int ks = a.k_splits > 8 ? 8 : a.k_splits;
+            for (; ks >= 2; --ks) {
+                if (cache[dev][ks] < 0) cache[dev][ks] = max_active_clusters(kern, dim3(64 + 32 * EW), Cfg::SMEM_BYTES, ks);
+                if (cache[dev][ks] >= base_tiles && base_tiles * ks <= sm_count()) break;
+            }
+            if (ks >= 2) {
+                GemmArgs b = a;
+                b.k_splits = ks;
+                AF3_CHECK_CUDA(launch_kernel_cluster(kern, dim3(base_tiles * ks), dim3(64 + 32 * EW), Cfg::SMEM_BYTES, stream, ks, mr, mc, mo,
+                                                     mres, b));
+                return 0;
+            }
+            // no cluster size fits: global-memory reduction (below) when a workspace was given, else no split
+            GemmArgs b = a;
+            b.cluster_reduce = 0;
+            if (!b.ws) b.k_splits = 1;
+            const int tiles_b = base_tiles * b.k_splits;
+            AF3_CHECK_CUDA(launch_kernel(kern, dim3(tiles_b < sm_count() ? tiles_b : sm_count()), dim3(64 + 32 * EW), Cfg::SMEM_BYTES, stream, mr,
+                                         mc, mo, mres, b));
+            return 0;
+        }
     }
     const int tiles = a.num_r_tiles * a.num_c_tiles * (SWAP && a.k_splits > 1 ? a.k_splits : 1);
     const int grid = tiles < sm_count() ? tiles : sm_count();
@@ -906,7 +1011,9 @@ int gemm_bf16(cudaStream_t stream, const bf16* x, int ldx, const bf16* w, int ld
     if (nf) {
         AF3_REQUIRE(n_tok <= 64, "gemm: RMSNorm fusion exists for the few-token (decode) GEMMs only");
         if (nf->norm_w) {
-            AF3_REQUIRE(nf->norm_part && nf->norm_parts > 0 && nf->norm_ld >= n_tok, "gemm: fused RMSNorm needs the sum-of-squares partials");
+            AF3_REQUIRE(nf->norm_part && nf->norm_parts > 0 && nf->norm_parts <= 32 && nf->norm_ld >= 32 && nf->norm_ld % 4 == 0 &&
+                            (reinterpret_cast<uintptr_t>(nf->norm_part) & 15) == 0,
+                        "gemm: fused RMSNorm needs <= 32 sum-of-squares partials per token in 16-byte aligned rows of >= 32 floats");
             AF3_REQUIRE(K % 64 == 0 && (reinterpret_cast<uintptr_t>(nf->norm_w) & 15) == 0, "gemm: fused RMSNorm needs K % 64 == 0 and a 16-byte aligned weight");
             a.norm_w = nf->norm_w;
             a.norm_part = nf->norm_part;
@@ -915,7 +1022,7 @@ int gemm_bf16(cudaStream_t stream, const bf16* x, int ldx, const bf16* w, int ld
             a.norm_eps = nf->norm_eps;
         }
         if (nf->sumsq_out) {
-            AF3_REQUIRE(nf->sumsq_ld >= n_tok && !(flags & (EPI_F32OUT | EPI_SWIGLU | EPI_ROPE)) && (ldo % 8) == 0 && res_period == 0 &&
+            AF3_REQUIRE(nf->sumsq_ld >= ceil_div(n_feat, 128) && !(flags & (EPI_F32OUT | EPI_SWIGLU | EPI_ROPE)) && (ldo % 8) == 0 && res_period == 0 &&
                             (!(flags & EPI_RESID) || (ld_res % 8) == 0),
                         "gemm: sum-of-squares output needs the token-major bf16 epilogue");
             a.sumsq_out = nf->sumsq_out;
@@ -995,6 +1102,11 @@ int gemm_bf16(cudaStream_t stream, const bf16* x, int ldx, const bf16* w, int ld
             a.k_splits = s;
             a.ws = reinterpret_cast<float*>(workspace);
             a.counters = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(workspace) + (8u << 20));
+            // reduce through distributed shared memory inside a thread-block cluster when the token-major bf16 epilogue applies
+            // (AF3_CLUSTER_REDUCE=0: the global-memory reduction of round 1, kept as fallback and for A/B runs)
+            const char* e = getenv("AF3_CLUSTER_REDUCE");
+            const bool transposed_epi = !(flags & EPI_F32OUT) && (ldo % 8) == 0 && (!(flags & EPI_RESID) || ((ld_res % 8) == 0 && res_period == 0));
+            a.cluster_reduce = (!(e && e[0] == '0') && transposed_epi) ? 1 : 0;
         }
     }
     AF3_REQUIRE(!a.norm_w || a.num_r_tiles * a.num_c_tiles * a.k_splits <= sm_count(), "gemm: fused RMSNorm needs one work item per CTA");

@@ -344,12 +344,13 @@ class Qwen2ForCausalLM(nn.Module):
         # per-row-tile sums of squares of the rows they store; the next q/k/v / gate-up GEMM normalises its activation tiles in
         # shared memory.  55 of the 57 norm launches of a step (and two dependency hops each) disappear; only layer 0's input
         # norm (input from the embedding gather) and the final norm stay kernels.  AF3_FUSE_NORM=0: the round-1 chain (A/B runs).
-        fuse_norm = fused_qkv and self.hid % 64 == 0 and os.environ.get("AF3_FUSE_NORM", "1") != "0"
+        fuse_norm = fused_qkv and self.hid % 64 == 0 and self.hid <= 4096 and os.environ.get("AF3_FUSE_NORM", "1") != "0"
+        n_parts = -(-self.hid // 128)
         if fused_qkv:
             rope_cs = ops.rope_table(B, D, cache.pos_dev, cache.kv_start, self._inv_freq)
         ss = ss_attn = ss_mlp = None   # ss: partials describing the CURRENT residual stream h (None -> stand-alone norm kernel)
         if fuse_norm:
-            ss_attn, ss_mlp = ops.sumsq_buffer(self.hid, B, h.device), ops.sumsq_buffer(self.hid, B, h.device)
+            ss_attn, ss_mlp = ops.sumsq_buffer(B, h.device), ops.sumsq_buffer(B, h.device)
         y = None
         for li, (l, (wqkv, bqkv, wgu)) in enumerate(zip(self.model.layers, self._packed)):
             kc, vc = cache.k[li], cache.v[li]
@@ -359,7 +360,7 @@ class Qwen2ForCausalLM(nn.Module):
                     # q/k/v projection with RoPE + KV append in the GEMM epilogue (rope table: once per step, above)
                     if ss is not None:
                         qkv = ops.qkv_rope_linear(h, wqkv, bqkv, kc, vc, H=H, Hkv=Hkv, D=D, rope_cs=rope_cs, pos_dev=cache.pos_dev,
-                                                  norm=(l.input_layernorm.weight, ss, self.eps))
+                                                  norm=(l.input_layernorm.weight, ss, n_parts, self.eps))
                     else:
                         y = ops.rmsnorm(h, l.input_layernorm.weight, self.eps, out=y)
                         qkv = ops.qkv_rope_linear(y, wqkv, bqkv, kc, vc, H=H, Hkv=Hkv, D=D, rope_cs=rope_cs, pos_dev=cache.pos_dev)
@@ -382,7 +383,7 @@ class Qwen2ForCausalLM(nn.Module):
                               kv_start=cache.kv_start)
             if fuse_norm:
                 ops.linear(a, l.self_attn.o_proj.weight, resid=h, out=h, sumsq_out=ss_attn)
-                g = ops.swiglu_linear(h, wgu, self.inter, norm=(l.post_attention_layernorm.weight, ss_attn, self.eps))
+                g = ops.swiglu_linear(h, wgu, self.inter, norm=(l.post_attention_layernorm.weight, ss_attn, n_parts, self.eps))
                 ops.linear(g, l.mlp.down_proj.weight, resid=h, out=h, sumsq_out=ss_mlp)
                 ss = ss_mlp
             else:

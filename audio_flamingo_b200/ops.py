@@ -82,23 +82,25 @@ def gemm_workspace(device):
 
 
 def _fusion(norm, sumsq_out):
-    """ctypes af3_gemm_fusion or None.  norm = (weight bf16 [K], partials fp32 [parts, ld], eps); sumsq_out fp32 [row tiles, ld]."""
+    """ctypes af3_gemm_fusion or None.  norm = (weight bf16 [K], partials fp32 [n_tok, >= 32], number of partials per row, eps);
+    sumsq_out fp32 [n_tok, >= 32] (see sumsq_buffer)."""
     if norm is None and sumsq_out is None:
         return None
     f = _lib.GemmFusion()
     if norm is not None:
-        wn, part, eps = norm
+        wn, part, nparts, eps = norm
         _req(wn, bf16, "norm weight"), _req(part, torch.float32, "norm partials")
-        f.norm_weight, f.norm_sumsq, f.norm_parts, f.norm_ld, f.norm_eps = ptr(wn), ptr(part), part.shape[0], part.stride(0), float(eps)
+        f.norm_weight, f.norm_sumsq, f.norm_parts, f.norm_ld, f.norm_eps = ptr(wn), ptr(part), int(nparts), part.stride(0), float(eps)
     if sumsq_out is not None:
         _req(sumsq_out, torch.float32, "sumsq_out")
         f.sumsq_out, f.sumsq_ld = ptr(sumsq_out), sumsq_out.stride(0)
     return f
 
 
-def sumsq_buffer(n_feat, n_tok, device):
-    """fp32 [ceil(n_feat / 128), n_tok]: per-row-tile sums of squares a residual GEMM emits for the next fused RMSNorm."""
-    return torch.empty(((n_feat + 127) // 128, n_tok), device=device, dtype=torch.float32)
+def sumsq_buffer(n_tok, device):
+    """fp32 [n_tok, 32]: per token, one sum of squares per 128-feature row tile of what a residual GEMM stores (up to 32 tiles =
+    4096 features), consumed by the next GEMM's fused RMSNorm."""
+    return torch.empty((n_tok, 32), device=device, dtype=torch.float32)
 
 
 def linear(x, w, bias=None, *, gelu=False, resid=None, res_period=0, out=None, out_f32=False, norm=None, sumsq_out=None):

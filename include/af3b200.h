@@ -132,19 +132,20 @@ int af3_rope_table(void* stream, float* rope_cs, int B, int D, const int* pos_de
 /* Qwen2RMSNorm ([O] Q2M:258-263) fused ACROSS two few-token (n_tok <= 64) GEMMs of the decode step, so that the norm kernel and
  * its two dependency hops leave the step's kernel chain (profiles/r02b_decode_timeline.md: 57 norm launches x 2.9 us per step):
  *   producer side (a GEMM with the bf16 token-major epilogue, typically the residual o / down projection): sumsq_out
- *     [ceil(n_feat / 128)][sumsq_ld] receives, per 128-feature row tile and token, the sum of squares of the bf16 values the
- *     GEMM stored;
+ *     [n_tok][sumsq_ld] receives, per token, one sum of squares per 128-feature row tile (entry [tok][tile]) of the bf16
+ *     values the GEMM stored;
  *   consumer side (the next q/k/v or gate/up projection): x is the UN-normalised residual stream; with norm_weight [K] bf16 and the
- *     producer's partials (norm_sumsq [norm_parts][norm_ld]) the kernel computes rstd = rsqrt(sum / K + eps) per token and feeds
- *     the tensor cores  norm_weight[k] * bf16(x[k] * rstd)  -- the reference's two roundings -- instead of x.
+ *     producer's partials (norm_sumsq [n_tok][norm_ld], the first norm_parts <= 32 entries of a row are summed, norm_ld >= 32 and a
+ *     multiple of 4, rows 16-byte aligned) the kernel computes rstd = rsqrt(sum / K + eps) per token and feeds the tensor cores
+ *     norm_weight[k] * bf16(x[k] * rstd)  -- the reference's two roundings -- instead of x.
  * Either side may be left out (NULL pointers).  K % 64 == 0; the consumer must fit one work item per SM (true for the decode
  * shapes; checked).  Deterministic (fixed summation order). */
 typedef struct af3_gemm_fusion {
     const void* norm_weight; /* bf16 [K] or NULL */
-    const float* norm_sumsq; /* [norm_parts][norm_ld] */
+    const float* norm_sumsq; /* [n_tok][norm_ld], norm_parts used per row */
     int norm_parts, norm_ld;
     float norm_eps;
-    float* sumsq_out;        /* [ceil(n_feat/128)][sumsq_ld] or NULL */
+    float* sumsq_out;        /* [n_tok][sumsq_ld >= ceil(n_feat/128)] or NULL */
     int sumsq_ld;
 } af3_gemm_fusion;
 /* af3_gemm_bf16_ws plus the fusion descriptor (NULL = plain). */

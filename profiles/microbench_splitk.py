@@ -37,7 +37,10 @@ def run_shape(name, N, K, mode, copies=12, iters=48):
             ops.linear(x, w, resid=out, out=out)
 
     rows = []
-    for ks in (1, 2, 3, 4, 5, 6, 8):
+    for cluster, ks in [(c, k) for c in ("1", "0") for k in (1, 2, 3, 4, 5, 6, 8)]:
+        if cluster == "0" and ks == 1:
+            continue
+        os.environ["AF3_CLUSTER_REDUCE"] = cluster   # 1: partials through distributed shared memory (cluster), 0: through L2 + counters
         os.environ["AF3_KSPLIT"] = str(ks)
         for i in range(4):
             run(i)
@@ -71,10 +74,11 @@ def run_shape(name, N, K, mode, copies=12, iters=48):
             t_wait = int(m[live, 1][m[live, 1] > 0].min())
             stream.append((int(m[live, 2].max()) - t_wait) / 1e3)
             tail.append((int(m[live, 3].max()) - int(m[live, 2].max())) / 1e3)
-        rows.append({"k_splits_requested": ks, "ctas": ctas, "us_per_launch": round(us, 2), "tbs": round(N * K * 2 / us / 1e6, 2),
+        rows.append({"reduce": "cluster/dsmem" if cluster == "1" else "global memory", "k_splits_requested": ks, "ctas": ctas, "us_per_launch": round(us, 2), "tbs": round(N * K * 2 / us / 1e6, 2),
                      "stream_us_median": round(statistics.median(stream), 2), "tail_us_median": round(statistics.median(tail), 2)})
         del g
     os.environ.pop("AF3_KSPLIT", None)
+    os.environ.pop("AF3_CLUSTER_REDUCE", None)
     return {"shape": name, "n_feat": N, "K": K, "epilogue": mode, "weight_bytes": N * K * 2, "ideal_us_at_6573_gbs": round(N * K * 2 / 6573e3, 2),
             "sweep": rows}
 
