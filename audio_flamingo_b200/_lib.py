@@ -10,7 +10,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 _LIB_PATH = _PKG / "libaf3b200.so"
 
-EPI_BIAS, EPI_GELU, EPI_RESID, EPI_SWIGLU, EPI_F32OUT = 1, 2, 4, 8, 16
+EPI_BIAS, EPI_GELU, EPI_RESID, EPI_SWIGLU, EPI_F32OUT, EPI_SWIGLU_CONCAT = 1, 2, 4, 8, 16, 64
 
 _p, _i, _f, _i64, _sz = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_size_t
 

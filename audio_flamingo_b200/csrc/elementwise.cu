@@ -50,10 +50,10 @@ layernorm_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const bf16* _
     for (int i = 0; i < NV; ++i) {
         const int c = lane + 32 * i;
         if (c < nchunk) {
-            unpack8(xp[c], v[i]);
+            unpack8(__ldcs(xp + c), v[i]);   // streaming: the row is read once per launch
             if (POOL) {
                 float b[8];
-                unpack8(xp[c + nchunk], b);
+                unpack8(__ldcs(xp + c + nchunk), b);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) v[i][e] = bf16_round((v[i][e] + b[e]) * 0.5f);
             }
@@ -87,7 +87,7 @@ layernorm_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const bf16* _
             unpack8(__ldg(bp + c), b);
 #pragma unroll
             for (int e = 0; e < 8; ++e) o[e] = (v[i][e] - mean) * rstd * g[e] + b[e];
-            yp[c] = pack8(o);
+            yp[c] = pack8(o);   // default policy: the next GEMM reads y right away (L2)
         }
     }
 }
@@ -134,7 +134,7 @@ int avgpool_layernorm(cudaStream_t stream, const bf16* x, bf16* y, const bf16* g
 // decoder that is 56 instead of 112 live registers per thread, which doubles the resident warps per SM.  Round 1 measured this
 // kernel at 0.37 of the HBM peak (ncu: 127 registers, 16 warps per SM): every warp loads its whole row, reduces, then stores,
 // so the bytes in flight per SM are (resident warps) x (row bytes) x (share of a warp's life spent loading) -- occupancy IS the
-// bandwidth here.  Streaming cache hints: x is read once and y written once per launch.
+// bandwidth here.  x is read with the streaming hint (read once per launch).
 template <int NV>
 __global__ void __launch_bounds__(256)
 rmsnorm_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const bf16* __restrict__ weight, int rows, int dim,
@@ -178,7 +178,7 @@ rmsnorm_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const bf16* __r
             unpack8(__ldg(wp + c), w);
 #pragma unroll
             for (int e = 0; e < 8; ++e) o[e] = w[e] * bf16_round(f[e] * rstd);
-            __stcs(yp + c, pack8(o));
+            yp[c] = pack8(o);   // default policy: the GEMM that follows re-reads y, part of it still in L2
         }
     }
     if (threadIdx.x == 0) trace_mark(trace, 3);

@@ -23,7 +23,8 @@
 
 namespace af3 {
 
-enum : int { EPI_BIAS = 1, EPI_GELU = 2, EPI_RESID = 4, EPI_SWIGLU = 8, EPI_F32OUT = 16, EPI_ROPE = 32 };
+enum : int { EPI_BIAS = 1, EPI_GELU = 2, EPI_RESID = 4, EPI_SWIGLU = 8, EPI_F32OUT = 16, EPI_ROPE = 32,
+              EPI_SWIGLU_CONCAT = 64 /* host-side only: weight rows are [gate; up], not interleaved (stripped before dispatch) */ };
 
 struct GemmArgs {
     int R, C, K;  // extents of row operand, col operand, reduction
@@ -48,11 +49,14 @@ struct GemmArgs {
     const int* rope_pos;     // device int: cache slot of this step
     int rope_H, rope_Hkv, rope_Tmax;
     int tma_epi;    // normal mode: stage the output tile in smem and write it with TMA (coalesced); residual via TMA too
+    // SwiGLU weight layout: 0 = gate / up interleaved in blocks of 128 rows (af3_pack_gate_up); > 0 = plain concatenation
+    // [gate (n_feat rows); up (n_feat rows)], the value being the first up row -- the two 128-row halves of a tile are then fetched
+    // by two TMA boxes, and gate_proj.weight / up_proj.weight can simply be VIEWS of the fused matrix (no second copy in HBM)
+    int swiglu_up_row0;
     int k_splits;
-    // cluster_reduce: the k_splits CTAs of a tile form a thread-block cluster and exchange their fp32 partial tiles through
-    // distributed shared memory: CTA q of the cluster receives everyone's partials for ITS slice of the 32 tokens, sums them in
-    // split order (deterministic) and runs the fused epilogue for that slice.  No global workspace, no fences, no atomics, no
-    // L2 round trips in the tail (round 2: the split-K tails were the largest loss of the decode step).
+    // cluster_reduce (EXPERIMENT, off by default -- measured slower, see gemm_bf16()): the k_splits CTAs of a tile form a thread-block
+    // cluster and exchange their fp32 partial tiles through distributed shared memory: CTA q of the cluster receives everyone's
+    // partials for ITS slice of the 32 tokens, sums them in split order (deterministic) and runs the fused epilogue for that slice.
     int cluster_reduce;
     float* ws;      // [tiles][k_splits][BN][128] fp32
     int* counters;  // [tiles], zero on entry, reset to zero by the reducing CTA
@@ -155,7 +159,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
             mbar_init(&tempty[i], 32 * EW);
         }
         for (int i = 0; i < 8; ++i) mbar_init(&rbar[i], 1);
-        for (int i = 0; i < STAGES; ++i) mbar_init(&xf[i], 32 * EW);
+        for (int i = 0; i < STAGES; ++i) mbar_init(&xf[i], 1);
         if (a.tma_epi) {
             tma_prefetch_desc(&map_out);
             if ((((EPI >= 0) ? EPI : a.flags) & EPI_RESID) && a.res_period == 0) tma_prefetch_desc(&map_res);
@@ -201,7 +205,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
                         uint8_t* sR = smem + prefetched * Cfg::STAGE_BYTES;
 #pragma unroll
                         for (int na = 0; na < NA; ++na)
-                            tma_load_2d(sR + na * 128 * BK * 2, &map_r, &full[prefetched], kb * BK, (r * NA + na) * 128);
+                            tma_load_2d(sR + na * 128 * BK * 2, &map_r, &full[prefetched], kb * BK,
+                                        a.swiglu_up_row0 ? na * a.swiglu_up_row0 + r * 128 : (r * NA + na) * 128);
                     }
                 }
             }
@@ -219,9 +224,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
                         mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
 #pragma unroll
                         for (int na = 0; na < NA; ++na)
-                            tma_load_2d(sR + na * 128 * BK * 2, &map_r, &full[stage], kb * BK, (r * NA + na) * 128);
+                            tma_load_2d(sR + na * 128 * BK * 2, &map_r, &full[stage], kb * BK,
+                                        (SWAP && a.swiglu_up_row0) ? na * a.swiglu_up_row0 + r * 128 : (r * NA + na) * 128);
                     }
-                    tma_load_2d(sC, &map_c, &full[stage], kb * BK, c * BN);
+                    if (!SWAP && a.swiglu_up_row0) {   // [gate; up] rows: two 128-row boxes make up the 256-column tile
+                        tma_load_2d(sC, &map_c, &full[stage], kb * BK, c * 128);
+                        tma_load_2d(sC + 128 * BK * 2, &map_c, &full[stage], kb * BK, a.swiglu_up_row0 + c * 128);
+                    } else {
+                        tma_load_2d(sC, &map_c, &full[stage], kb * BK, c * BN);
+                    }
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -297,19 +308,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
         if (threadIdx.x == 64) trace_mark(a.trace, 1);
         if constexpr (SWAP && EW == 4) {
             if (a.norm_w) {
-                // ---- fused RMSNorm of the activation tiles (this CTA's single work item): thread -> token et / 4, 16-byte chunks
-                //      2 (et % 4), 2 (et % 4) + 1 of the 64-wide k block
+                // ---- fused RMSNorm of the activation tiles (this CTA's single work item).  WARP-granular: epilogue warp ew rewrites
+                //      the k blocks ew, ew + 4, ... of the CTA's K range, lane = token (128-byte row of the swizzled [32][64] tile), so four
+                //      tiles are in flight at once.  (The first version had all 128 threads walk the k blocks one after the other: at
+                //      ~0.8 us per block -- wait, 2 LDS, math, 2 STS, proxy fence, arrive -- 56 blocks took longer than the weights
+                //      needed to stream, profiles/r02e_decode_timeline_*.md.)
                 const int t0 = blockIdx.x;
                 int r0, c0;
                 tile_coords(t0 / k_splits, a, r0, c0);
                 const int sp0 = t0 % k_splits;
-                const int et = threadIdx.x - 64, tt = et >> 2, ch0 = (et & 3) * 2;
-                const int tokg = c0 * BN + tt;
+                const int ew = warp - 2;
+                const int tokg = c0 * BN + lane;
                 float ss = 0.f;
                 if (t0 < num_tiles && tokg < a.n_tok) {
-                    // all partials of the token in ONE round trip: 8 independent 16-byte loads (<= 32 partials, zero padded by
-                    // the count test), then a fixed-order sum.  (A loop of dependent scalar loads cost 7 L2 round trips = 5 us per
-                    // launch in the first version, profiles/r02d_decode_timeline_fused_norm_v1.md.)
+                    // all partials of the token in ONE round trip: 8 independent 16-byte loads (<= 32 partials), then a fixed-order sum
                     const float4* pp = reinterpret_cast<const float4*>(a.norm_part + static_cast<size_t>(tokg) * a.norm_ld);
                     float4 pv[8];
 #pragma unroll
@@ -325,43 +337,33 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
                 }
                 const float rstd = (tokg < a.n_tok) ? rsqrtf(ss / static_cast<float>(a.K) + a.norm_eps) : 0.f;
                 if (t0 < num_tiles) {
-                    int stage = 0;
-                    uint32_t phase = 0;
-                    const int kb0 = kb_lo(sp0), kb1 = kb_lo(sp0 + 1);
+                    const int kb0 = kb_lo(sp0), nkb = kb_lo(sp0 + 1) - kb0;
                     const uint4* wv = reinterpret_cast<const uint4*>(a.norm_w);
-                    uint4 w0 = __ldg(wv + kb0 * 8 + ch0), w1 = __ldg(wv + kb0 * 8 + ch0 + 1);
-                    for (int kb = kb0; kb < kb1; ++kb) {
-                        uint4 nw0 = w0, nw1 = w1;
-                        if (kb + 1 < kb1) {   // next k block's norm weights: in flight while this tile is rewritten
-                            nw0 = __ldg(wv + (kb + 1) * 8 + ch0);
-                            nw1 = __ldg(wv + (kb + 1) * 8 + ch0 + 1);
-                        }
+                    for (int i = ew; i < nkb; i += 4) {
+                        const int kb = kb0 + i, stage = i % STAGES;
+                        const uint32_t phase = (i / STAGES) & 1;
+                        uint4 wq[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) wq[j] = __ldg(wv + kb * 8 + j);   // same address in every lane: one L1 transaction
                         mbar_wait(&full[stage], phase);
-                        uint8_t* sX = smem + stage * Cfg::STAGE_BYTES + Cfg::R_BYTES + tt * 128;   // 128B-swizzled [BN][64] bf16 tile
-                        uint4* p0 = reinterpret_cast<uint4*>(sX + ((ch0 ^ (tt & 7)) << 4));
-                        uint4* p1 = reinterpret_cast<uint4*>(sX + (((ch0 + 1) ^ (tt & 7)) << 4));
-                        const uint4 x0 = *p0, x1 = *p1;
-                        auto norm8 = [&](const uint4& xv, const uint4& wq) {
+                        uint8_t* sX = smem + stage * Cfg::STAGE_BYTES + Cfg::R_BYTES + lane * 128;   // this token's row of the tile
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            uint4* px = reinterpret_cast<uint4*>(sX + ((j ^ (lane & 7)) << 4));
+                            const uint4 xv = *px;
                             const __nv_bfloat162* xh = reinterpret_cast<const __nv_bfloat162*>(&xv);
-                            const __nv_bfloat162* wh = reinterpret_cast<const __nv_bfloat162*>(&wq);
+                            const __nv_bfloat162* wh = reinterpret_cast<const __nv_bfloat162*>(&wq[j]);
                             uint32_t o[4];
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
                                 const float2 xf2 = __bfloat1622float2(xh[e]), wf = __bfloat1622float2(wh[e]);
                                 o[e] = pack_bf16x2(wf.x * bf16_round(xf2.x * rstd), wf.y * bf16_round(xf2.y * rstd));
                             }
-                            return make_uint4(o[0], o[1], o[2], o[3]);
-                        };
-                        *p0 = norm8(x0, w0);
-                        *p1 = norm8(x1, w1);
-                        fence_proxy_async_smem();
-                        mbar_arrive(&xf[stage]);
-                        w0 = nw0;
-                        w1 = nw1;
-                        if (++stage == STAGES) {
-                            stage = 0;
-                            phase ^= 1;
+                            *px = make_uint4(o[0], o[1], o[2], o[3]);
                         }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&xf[stage]);
                     }
                 }
             }
@@ -994,6 +996,9 @@ int gemm_bf16(cudaStream_t stream, const bf16* x, int ldx, const bf16* w, int ld
     AF3_REQUIRE(!(flags & EPI_BIAS) || bias, "gemm: bias flag without pointer");
     AF3_REQUIRE(!(flags & EPI_RESID) || resid, "gemm: residual flag without pointer");
     const bool swiglu = flags & EPI_SWIGLU;
+    const bool concat = swiglu && (flags & EPI_SWIGLU_CONCAT);
+    AF3_REQUIRE(!(flags & EPI_SWIGLU_CONCAT) || (swiglu && n_feat % 128 == 0), "gemm: the [gate; up] layout needs SwiGLU and n_feat % 128 == 0");
+    flags &= ~EPI_SWIGLU_CONCAT;
     const int w_rows = swiglu ? 2 * ceil_div(n_feat, 128) * 128 : n_feat;
     GemmArgs a{};
     a.K = K;
@@ -1006,6 +1011,7 @@ int gemm_bf16(cudaStream_t stream, const bf16* x, int ldx, const bf16* w, int ld
     a.ld_res = ld_res;
     a.res_period = res_period;
     a.flags = flags;
+    a.swiglu_up_row0 = concat ? n_feat : 0;
     a.k_splits = 1;
     a.trace = trace_next_slot();
     if (nf) {
@@ -1057,7 +1063,7 @@ int gemm_bf16(cudaStream_t stream, const bf16* x, int ldx, const bf16* w, int ld
             a.group_r = static_cast<int>(g < 8 ? 8 : (g > 256 ? 256 : g));
         }
         if (int e = make_tmap_2d(&mx, x, K, n_tok, ldx, BK, 128)) return e;
-        if (int e = make_tmap_2d(&mw, w, K, w_rows, ldw, BK, BN)) return e;
+        if (int e = make_tmap_2d(&mw, w, K, w_rows, ldw, BK, concat ? 128 : BN)) return e;
         // smem-staged TMA-store epilogue whenever the output (and residual) layout allows 16-byte-aligned rows
         const bool res_plain = (flags & EPI_RESID) && res_period == 0;
         a.tma_epi = !(flags & EPI_F32OUT) && (ldo % 8 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) &&
@@ -1104,9 +1110,13 @@ int gemm_bf16(cudaStream_t stream, const bf16* x, int ldx, const bf16* w, int ld
             a.counters = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(workspace) + (8u << 20));
             // reduce through distributed shared memory inside a thread-block cluster when the token-major bf16 epilogue applies
             // (AF3_CLUSTER_REDUCE=0: the global-memory reduction of round 1, kept as fallback and for A/B runs)
+            // MEASURED SLOWER (profiles/r02e_microbench_splitk.json, profiles/r02e_decode_timeline_cluster_fused.md) and therefore
+            // opt-in (AF3_CLUSTER_REDUCE=1): the tail is 5.4 us against 3.5 us through L2 -- 32 four-byte st.shared::cluster per thread
+            // run at ~2 B/clk per SM --, and a cluster can only become resident when k_splits SMs of one GPC are free, which costs the
+            // early (pre-dependency) weight prefetch under programmatic dependent launch.
             const char* e = getenv("AF3_CLUSTER_REDUCE");
             const bool transposed_epi = !(flags & EPI_F32OUT) && (ldo % 8) == 0 && (!(flags & EPI_RESID) || ((ld_res % 8) == 0 && res_period == 0));
-            a.cluster_reduce = (!(e && e[0] == '0') && transposed_epi) ? 1 : 0;
+            a.cluster_reduce = ((e && e[0] == '1') && transposed_epi) ? 1 : 0;
         }
     }
     AF3_REQUIRE(!a.norm_w || a.num_r_tiles * a.num_c_tiles * a.k_splits <= sm_count(), "gemm: fused RMSNorm needs one work item per CTA");

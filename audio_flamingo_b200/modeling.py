@@ -310,12 +310,25 @@ class Qwen2ForCausalLM(nn.Module):
         self._inv_freq = None
 
     def pack_weights(self):
+        """Fused q/k/v and gate/up matrices for the kernels.  The nn.Linear parameters of the reference's module tree are then
+        re-pointed at VIEWS of the fused matrices (same values, same state_dict): the decoder's projection weights exist once in HBM
+        (round 1 kept the originals next to the packed copies, +8.5 GB), and an in-place update of a parameter updates what the
+        kernels read.  gate/up need intermediate_size % 128 == 0 for the view trick ([gate; up] layout, AF3_EPI_SWIGLU_CONCAT);
+        otherwise the 128-row interleaved copy of round 1 is used."""
         P = []
+        HD, KD = self.H * self.D, self.Hkv * self.D
+        self._swiglu_concat = self.inter % 128 == 0
         for l in self.model.layers:
             a, m = l.self_attn, l.mlp
             wqkv = torch.cat([a.q_proj.weight.detach(), a.k_proj.weight.detach(), a.v_proj.weight.detach()], 0).contiguous()
             bqkv = torch.cat([a.q_proj.bias.detach(), a.k_proj.bias.detach(), a.v_proj.bias.detach()], 0).contiguous()
-            wgu = ops.pack_gate_up(m.gate_proj.weight.detach().contiguous(), m.up_proj.weight.detach().contiguous())
+            a.q_proj.weight.data, a.k_proj.weight.data, a.v_proj.weight.data = wqkv[:HD], wqkv[HD:HD + KD], wqkv[HD + KD:]
+            a.q_proj.bias.data, a.k_proj.bias.data, a.v_proj.bias.data = bqkv[:HD], bqkv[HD:HD + KD], bqkv[HD + KD:]
+            if self._swiglu_concat:
+                wgu = torch.cat([m.gate_proj.weight.detach(), m.up_proj.weight.detach()], 0).contiguous()
+                m.gate_proj.weight.data, m.up_proj.weight.data = wgu[: self.inter], wgu[self.inter:]
+            else:
+                wgu = ops.pack_gate_up(m.gate_proj.weight.detach().contiguous(), m.up_proj.weight.detach().contiguous())
             P.append((wqkv, bqkv, wgu))
         self._packed = P
         # Qwen2RotaryEmbedding.compute_default_rope_parameters, evaluated on the CPU like the reference (Q2M:86-89)
@@ -383,13 +396,14 @@ class Qwen2ForCausalLM(nn.Module):
                               kv_start=cache.kv_start)
             if fuse_norm:
                 ops.linear(a, l.self_attn.o_proj.weight, resid=h, out=h, sumsq_out=ss_attn)
-                g = ops.swiglu_linear(h, wgu, self.inter, norm=(l.post_attention_layernorm.weight, ss_attn, n_parts, self.eps))
+                g = ops.swiglu_linear(h, wgu, self.inter, norm=(l.post_attention_layernorm.weight, ss_attn, n_parts, self.eps),
+                                      concat=self._swiglu_concat)
                 ops.linear(g, l.mlp.down_proj.weight, resid=h, out=h, sumsq_out=ss_mlp)
                 ss = ss_mlp
             else:
                 ops.linear(a, l.self_attn.o_proj.weight, resid=h, out=h)
                 y = ops.rmsnorm(h, l.post_attention_layernorm.weight, self.eps, out=y)
-                g = ops.swiglu_linear(y, wgu, self.inter)
+                g = ops.swiglu_linear(y, wgu, self.inter, concat=self._swiglu_concat)
                 ops.linear(g, l.mlp.down_proj.weight, resid=h, out=h)
         return h
 

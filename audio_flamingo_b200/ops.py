@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import EPI_BIAS, EPI_F32OUT, EPI_GELU, EPI_RESID, EPI_SWIGLU, check, ptr, stream_ptr
+from ._lib import EPI_BIAS, EPI_F32OUT, EPI_GELU, EPI_RESID, EPI_SWIGLU, EPI_SWIGLU_CONCAT, check, ptr, stream_ptr
 
 bf16 = torch.bfloat16
 
@@ -146,8 +146,9 @@ def pack_gate_up(gate, up):
     return packed
 
 
-def swiglu_linear(x, w_packed, n_feat, out=None, norm=None):
-    """out = silu(x @ gate.T) * (x @ up.T) with w_packed from pack_gate_up; norm: fused RMSNorm of x (few-token mode)."""
+def swiglu_linear(x, w_packed, n_feat, out=None, norm=None, concat=False):
+    """out = silu(x @ gate.T) * (x @ up.T).  w_packed: from pack_gate_up (128-row interleave), or with concat=True the plain
+    [gate; up] concatenation (n_feat % 128 == 0).  norm: fused RMSNorm of x (few-token mode)."""
     lib = _lib.load()
     _req(x, bf16, "x"), _req(w_packed, bf16, "w_packed")
     n_tok, K = x.shape
@@ -157,7 +158,8 @@ def swiglu_linear(x, w_packed, n_feat, out=None, norm=None):
     with _Timed(("gemm", n_tok, n_feat, K, EPI_SWIGLU)):
         check(
             lib.af3_gemm_bf16_fused(stream_ptr(), ptr(x), x.stride(0), ptr(w_packed), w_packed.stride(0), ptr(out), out.stride(0),
-                                    n_tok, n_feat, K, EPI_SWIGLU, None, None, 0, 0, None, 0, C.byref(fus) if fus is not None else None),
+                                    n_tok, n_feat, K, EPI_SWIGLU | (EPI_SWIGLU_CONCAT if concat else 0), None, None, 0, 0, None, 0,
+                                    C.byref(fus) if fus is not None else None),
             "af3_gemm_bf16(swiglu)",
         )
     _count(1)

@@ -52,10 +52,12 @@ int af3_trace_seq(void);
 #define AF3_EPI_RESID 4
 #define AF3_EPI_SWIGLU 8
 #define AF3_EPI_F32OUT 16
+#define AF3_EPI_SWIGLU_CONCAT 64 /* with AF3_EPI_SWIGLU: w is [gate (n_feat rows); up (n_feat rows)], n_feat % 128 == 0 */
 
 /* out[tok, feat] = epi( x[tok,:] . w[feat,:] ), tcgen05 tensor cores.  Replaces F.linear at
  * [O] AF3M:111-114,141,153-154,204-205,398-402; Q2M:41-48,199-202,474-475 and F.conv1d (as im2col GEMM) at
- * AF3M:343-344.  With AF3_EPI_SWIGLU, w holds gate/up rows interleaved in blocks of 128 (see af3_pack_gate_up)
+ * AF3M:343-344.  With AF3_EPI_SWIGLU, w holds gate/up rows interleaved in blocks of 128 (see af3_pack_gate_up) -- or, with
+ * AF3_EPI_SWIGLU_CONCAT, simply concatenated [gate; up] (so the two nn.Linear weights can be views of one matrix) --
  * and out = silu(gate)*up with n_feat = intermediate size.  res_period > 0 adds resid[tok % res_period]. */
 int af3_gemm_bf16(void* stream, const void* x, int ldx, const void* w, int ldw, void* out, int ldo, int n_tok,
                   int n_feat, int K, int flags, const void* bias, const void* resid, int ld_res, int res_period);

@@ -53,6 +53,25 @@ for n_tok, tag in ((32, "few-token"), (200, "normal")):
     gg, uu = (xx.float() @ g.float().T).to(bf16).float(), (xx.float() @ u.float().T).to(bf16).float()
     ok(f"gemm swiglu {tag}", ops.swiglu_linear(xx, wp, 256), (torch.nn.functional.silu(gg).to(bf16).float() * uu))
 
+# ---- RMSNorm fused across two few-token GEMMs (producer partials + consumer transform), [gate; up] concat layout
+hh, wo2, rr = rnd(32, 512), rnd(512, 512, scale=0.05), rnd(32, 512)
+ssb = ops.sumsq_buffer(32, dev)
+hres = ops.linear(hh, wo2, resid=rr.clone(), sumsq_out=ssb)
+ok("fused norm: producer partials", ssb[:, :4], hres.float().pow(2).view(32, 4, 128).sum(-1), tol=1e-4)
+wn = (rnd(512, scale=0.3).float() + 1.0).to(bf16)
+w3, b3 = rnd(384, 512, scale=0.05), rnd(384, scale=0.3)
+ok("fused norm: consumer vs rmsnorm kernel", ops.linear(hres, w3, b3, norm=(wn, ssb, 4, 1e-6)), ops.linear(ops.rmsnorm(hres, wn, 1e-6), w3, b3))
+gc, uc = rnd(256, 512, scale=0.05), rnd(256, 512, scale=0.05)
+ok("fused norm + swiglu [gate; up]", ops.swiglu_linear(hres, torch.cat([gc, uc]).contiguous(), 256, norm=(wn, ssb, 4, 1e-6), concat=True),
+   ops.swiglu_linear(ops.rmsnorm(hres, wn, 1e-6), ops.pack_gate_up(gc, uc), 256))
+xx2 = rnd(200, 512)
+ok("swiglu [gate; up] token-major", ops.swiglu_linear(xx2, torch.cat([gc, uc]).contiguous(), 256, concat=True), ops.swiglu_linear(xx2, ops.pack_gate_up(gc, uc), 256), tol=1e-6)
+os.environ["AF3_CLUSTER_REDUCE"] = "1"
+os.environ["AF3_KSPLIT"] = "4"
+ok("gemm few-token cluster/DSMEM split-K x4 + resid (opt-in experiment)", ops.linear(xk, wk, resid=rk), (xk.float() @ wk.float().T).to(bf16).float() + rk.float())
+os.environ.pop("AF3_CLUSTER_REDUCE")
+os.environ.pop("AF3_KSPLIT")
+
 # ---- fused q/k/v + RoPE + KV append (few-token), stand-alone RoPE / append
 B, H, Hkv, D, K, Tmax = 4, 4, 2, 128, 256, 256
 xq, wq, bq = rnd(B, K), rnd((H + 2 * Hkv) * D, K, scale=0.05), rnd((H + 2 * Hkv) * D, scale=0.3)

@@ -254,3 +254,27 @@ def test_kv_capacity_planning_long_audio():
     spans = [shard_rows(len(windows), 2, r, windows) for r in range(2)]
     loads = [sum(windows[a:b]) for a, b in spans]
     assert spans[0][1] == spans[1][0] and abs(loads[0] - loads[1]) <= max(windows)
+
+
+def test_packing_leaves_one_copy_of_the_decoder_projections():
+    """pack_weights() re-points q/k/v (+ biases) and gate/up at views of the fused matrices the kernels read (the
+    decoder projections were kept twice, +8.5 GB at AF3-7B).  CPU-checkable: storages are shared, state_dict values unchanged."""
+    from oracle import af3_oracle as O
+
+    from audio_flamingo_b200.modeling import Qwen2ForCausalLM
+
+    cfg = O.hf_config("tiny")
+    torch.manual_seed(0)
+    lm = Qwen2ForCausalLM(cfg.text_config)
+    before = {k: v.clone() for k, v in lm.state_dict().items()}
+    lm.pack_weights()
+    after = lm.state_dict()
+    assert all(torch.equal(before[k], after[k]) for k in before)
+    l0, (wqkv, bqkv, wgu) = lm.model.layers[0], lm._packed[0]
+    for p in (l0.self_attn.q_proj.weight, l0.self_attn.k_proj.weight, l0.self_attn.v_proj.weight):
+        assert p.untyped_storage().data_ptr() == wqkv.untyped_storage().data_ptr()
+    assert l0.self_attn.v_proj.bias.untyped_storage().data_ptr() == bqkv.untyped_storage().data_ptr()
+    assert lm._swiglu_concat and l0.mlp.up_proj.weight.untyped_storage().data_ptr() == wgu.untyped_storage().data_ptr()
+    with torch.no_grad():
+        l0.mlp.gate_proj.weight[3, 5] = 7.0          # an in-place parameter update is what the kernels read
+    assert float(wgu[3, 5]) == 7.0

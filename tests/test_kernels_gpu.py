@@ -120,6 +120,10 @@ def test_gemm_swiglu(ops, M, F):
     up = (x.float() @ u.float().T).to(bf16)
     ref = (torch.nn.functional.silu(gate.float()).to(bf16).float() * up.float()).to(bf16)
     _close(out, ref, 2 * BF16_RTOL, 2e-3, f"swiglu M={M} F={F}")
+    if F % 128 == 0:
+        # [gate; up] layout (the two nn.Linear weights as views of one matrix): same tiles, same arithmetic -> bit-identical
+        out_c = ops.swiglu_linear(x, torch.cat([g, u], 0).contiguous(), F, concat=True)
+        assert torch.equal(out_c, out)
 
 
 def test_layernorm_and_pool(ops):
