@@ -309,8 +309,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
         if constexpr (SWAP && EW == 4) {
             if (a.norm_w) {
                 // ---- fused RMSNorm of the activation tiles (this CTA's single work item).  WARP-granular: epilogue warp ew rewrites
-                //      the k blocks ew, ew + 4, ... of the CTA's K range, lane = token (128-byte row of the swizzled [32][64] tile), so four
-                //      tiles are in flight at once.  (The first version had all 128 threads walk the k blocks one after the other: at
+                //      the k blocks that land in ring stages ew, ew + 4, lane = token (128-byte row of the swizzled [32][64] tile), so up
+                //      to four tiles are in flight at once.  (The first version had all 128 threads walk the k blocks one after the other: at
                 //      ~0.8 us per block -- wait, 2 LDS, math, 2 STS, proxy fence, arrive -- 56 blocks took longer than the weights
                 //      needed to stream, profiles/r02e_decode_timeline_*.md.)
                 const int t0 = blockIdx.x;
@@ -339,8 +339,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
                 if (t0 < num_tiles) {
                     const int kb0 = kb_lo(sp0), nkb = kb_lo(sp0 + 1) - kb0;
                     const uint4* wv = reinterpret_cast<const uint4*>(a.norm_w);
-                    for (int i = ew; i < nkb; i += 4) {
+                    // Ring stage s is always rewritten by the same warp (s % 4): a parity wait on full[s] can only tell consecutive
+                    // uses of a stage apart, so the warp that waits for use n must be the one that saw use n - 1.  (Assigning k blocks
+                    // round-robin, i % 4, let a warp skip a use of a 6-deep ring and race two uses ahead: deadlock at K = 3584.)
+                    for (int i = 0; i < nkb; ++i) {
                         const int kb = kb0 + i, stage = i % STAGES;
+                        if ((stage & 3) != ew) continue;
                         const uint32_t phase = (i / STAGES) & 1;
                         uint4 wq[8];
 #pragma unroll

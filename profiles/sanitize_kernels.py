@@ -64,6 +64,16 @@ ok("fused norm: consumer vs rmsnorm kernel", ops.linear(hres, w3, b3, norm=(wn, 
 gc, uc = rnd(256, 512, scale=0.05), rnd(256, 512, scale=0.05)
 ok("fused norm + swiglu [gate; up]", ops.swiglu_linear(hres, torch.cat([gc, uc]).contiguous(), 256, norm=(wn, ssb, 4, 1e-6), concat=True),
    ops.swiglu_linear(ops.rmsnorm(hres, wn, 1e-6), ops.pack_gate_up(gc, uc), 256))
+# deep K (32 k blocks > ring depth): every ring stage is reused several times by its owning warp
+hk_, wok, rrk = rnd(32, 256), rnd(2048, 256, scale=0.05), rnd(32, 2048)
+ssk = ops.sumsq_buffer(32, dev)
+hk2 = ops.linear(hk_, wok, resid=rrk.clone(), sumsq_out=ssk)
+wnk = (rnd(2048, scale=0.3).float() + 1.0).to(bf16)
+gk, uk = rnd(256, 2048, scale=0.03), rnd(256, 2048, scale=0.03)
+ok("fused norm + swiglu, K = 2048", ops.swiglu_linear(hk2, torch.cat([gk, uk]).contiguous(), 256, norm=(wnk, ssk, 16, 1e-6), concat=True),
+   ops.swiglu_linear(ops.rmsnorm(hk2, wnk, 1e-6), ops.pack_gate_up(gk, uk), 256))
+w3k, b3k = rnd(384, 2048, scale=0.03), rnd(384, scale=0.3)
+ok("fused norm, K = 2048, bias", ops.linear(hk2, w3k, b3k, norm=(wnk, ssk, 16, 1e-6)), ops.linear(ops.rmsnorm(hk2, wnk, 1e-6), w3k, b3k))
 xx2 = rnd(200, 512)
 ok("swiglu [gate; up] token-major", ops.swiglu_linear(xx2, torch.cat([gc, uc]).contiguous(), 256, concat=True), ops.swiglu_linear(xx2, ops.pack_gate_up(gc, uc), 256), tol=1e-6)
 os.environ["AF3_CLUSTER_REDUCE"] = "1"
