@@ -51,7 +51,7 @@ struct Attn2Cfg {
     static constexpr int NSTG = (D == 128) ? 4 : 6;         // K/V ring slots (one K or V tile each)
     static constexpr int TILE_BYTES = A2_BN * D * 2;
     static constexpr int Q_BYTES = 2 * A2_BM * D * 2;       // both Q tiles
-    static constexpr int SMEM_BYTES = Q_BYTES + NSTG * TILE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES = Q_BYTES + NSTG * TILE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 6144 /*half-row max / sum exchange (TPR = 2)*/;
     static constexpr int TMEM_COLS = 512;
 };
 
@@ -66,8 +66,14 @@ __device__ __forceinline__ void a2_tile_range(const Attn2Args& a, int b, int q0,
     if (j_hi < j_lo) j_hi = j_lo;
 }
 
-template <int D>
-__global__ void __launch_bounds__(320, 1)
+// TPR = threads per query row in the softmax groups.  1: 4 warps per group, whole row per thread (no exchange at all).
+// 2: 8 warps per group, each thread owns 64 of the 128 key columns, HOLDS them in registers (one TMEM pass instead of two) and the
+// two half-row maxima / sums are exchanged through shared memory with one 256-thread named barrier per tile.  The ncu profile of
+// TPR = 1 (profiles/r02c_ncu_attention_v2_d128.md) showed the softmax to be latency-bound per warp (1260 instructions per tile at
+// 0.18 IPC, two such warps per scheduler): TPR = 2 halves the per-thread chain and doubles the warps each scheduler can pick from.
+// Measured (profiles/r02i_microbench_attention.json): TPR = 2 is 7-12 % SLOWER than TPR = 1 on all three shapes, so TPR = 1 is the default.
+template <int D, int TPR>
+__global__ void __launch_bounds__(64 + 256 * TPR, 1)
 attention2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                   const __grid_constant__ CUtensorMap map_v, const Attn2Args a) {
     using Cfg = Attn2Cfg<D>;
@@ -85,6 +91,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     uint64_t* p_full = s_full + 2;        // [2]
     uint64_t* o_full = p_full + 2;        // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+    [[maybe_unused]] float* xch = reinterpret_cast<float*>(bars + 32);   // [2 groups][3: max parity 0 / max parity 1 / sums][2 halves][128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // heavy (late) causal row blocks first: the last wave is then made of the short ones
@@ -103,7 +110,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         }
         for (int g = 0; g < 2; ++g) {
             mbar_init(&s_full[g], 1);
-            mbar_init(&p_full[g], 128);
+            mbar_init(&p_full[g], 128 * TPR);
             mbar_init(&o_full[g], 1);
         }
         fence_barrier_init();
@@ -213,113 +220,109 @@ attention2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         }
         __syncwarp();
     } else {
-        // ---- softmax: group g = Q tile g, one thread per query row (= TMEM lane)
-        const int g = (warp - 2) >> 2;
-        const int qd = warp & 3;               // TMEM lane quarter this warp may touch
-        const int row = qd * 32 + lane;
-        const int q0g = q0 + g * A2_BM;
-        const int qi = q0g + row;
-        const int n_g = g ? nB : nA;
-        const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
-        const uint32_t s_col = tmem_S0 + g * A2_BN + lane_off;
-        const uint32_t o_col = tmem_O0 + g * D + lane_off;
-        const int kvl = a.kv_len ? min(a.kv_len[b], a.Tk) : a.Tk;
-        const int kvs = a.kv_start ? a.kv_start[b] : 0;
-        const int causal_hi = a.causal ? qi + (a.Tk - a.Tq) : 0x7fffffff;  // last visible key (inclusive)
-        const float sl2 = a.scale_log2;
-        float m_ref = -INFINITY, l_run = 0.f;
+        if constexpr (TPR == 2) {
+            // ---- softmax, two threads per query row: warp w of the group handles TMEM lane quarter (w & 3) and key columns
+            //      [half * 64, half * 64 + 64) with half = (w - first warp of the group) >> 2
+            const int sw = warp - 2;
+            const int g = sw >> 3;
+            const int half = (sw >> 2) & 1;
+            const int qd = warp & 3;
+            const int row = qd * 32 + lane;
+            const int q0g = q0 + g * A2_BM;
+            const int qi = q0g + row;
+            const int n_g = g ? nB : nA;
+            const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
+            const uint32_t s_col = tmem_S0 + g * A2_BN + lane_off;
+            constexpr int OC = D / 2;               // O columns owned by this thread (rescale / epilogue)
+            const uint32_t o_col = tmem_O0 + g * D + lane_off + half * OC;
+            const int kvl = a.kv_len ? min(a.kv_len[b], a.Tk) : a.Tk;
+            const int kvs = a.kv_start ? a.kv_start[b] : 0;
+            const int causal_hi = a.causal ? qi + (a.Tk - a.Tq) : 0x7fffffff;
+            const float sl2 = a.scale_log2;
+            const int cbase = half * 64;
+            float* xg = xch + g * 768;              // this group's exchange area: [3][2][128]
+            float m_ref = -INFINITY, l_run = 0.f;   // l_run: partial row sum over this thread's columns
 
-        for (int t = 0; t < n_g; ++t) {
-            const int k0 = (j_lo + t) * A2_BN;
-            mbar_wait(&s_full[g], t & 1);
-            tc_fence_after();
-            const bool need_mask = (k0 < kvs) || (k0 + A2_BN > kvl) || (a.causal && k0 + A2_BN - 1 > q0g + (a.Tk - a.Tq));
-            const int vlo = max(kvs - k0, 0);
-            const int vhi = min(min(kvl - 1, causal_hi) - k0, A2_BN - 1);
-            const uint32_t vspan = static_cast<uint32_t>(vhi - vlo);
-            const bool row_empty = vhi < vlo;
-            // ---- pass 1: row max (thread-local)
-            float m_tile;
-            {
+            for (int t = 0; t < n_g; ++t) {
+                const int k0 = (j_lo + t) * A2_BN;
+                mbar_wait(&s_full[g], t & 1);
+                tc_fence_after();
+                const bool need_mask = (k0 < kvs) || (k0 + A2_BN > kvl) || (a.causal && k0 + A2_BN - 1 > q0g + (a.Tk - a.Tq));
+                const int vlo = max(kvs - k0, 0);
+                const int vhi = min(min(kvl - 1, causal_hi) - k0, A2_BN - 1);
+                const uint32_t vspan = static_cast<uint32_t>(vhi - vlo);
+                const bool row_empty = vhi < vlo;
+                // the thread's 64 scores: ONE TMEM read, kept in registers for both the max and the exponentials
+                uint32_t s0[32], s1[32];
+                tmem_ld32(s_col + cbase, s0);
+                tmem_ld32(s_col + cbase + 32, s1);
+                tmem_ld_wait();
                 float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-                // not unrolled over the column chunks: the fully unrolled kernel was 64 KB of SASS and the softmax warps spent 19 %
-                // of their non-waiting samples on instruction-cache misses (stall_no_inst, profiles/r02c_ncu_attention_v2.md)
-#pragma unroll 1
-                for (int c = 0; c < 4; c += 2) {
-                    uint32_t v0[32], v1[32];
-                    tmem_ld32(s_col + c * 32, v0);
-                    tmem_ld32(s_col + c * 32 + 32, v1);
-                    tmem_ld_wait();
-                    if (need_mask) {
-#pragma unroll
-                        for (int e = 0; e < 32; e += 2) {
-                            const bool ok0 = static_cast<uint32_t>(c * 32 + e - vlo) <= vspan;
-                            const bool ok1 = static_cast<uint32_t>(c * 32 + e + 1 - vlo) <= vspan;
-                            const bool ok2 = static_cast<uint32_t>(c * 32 + 32 + e - vlo) <= vspan;
-                            const bool ok3 = static_cast<uint32_t>(c * 32 + 33 + e - vlo) <= vspan;
-                            mx0 = fmaxf(mx0, ok0 ? __uint_as_float(v0[e]) : -INFINITY);
-                            mx1 = fmaxf(mx1, ok1 ? __uint_as_float(v0[e + 1]) : -INFINITY);
-                            mx2 = fmaxf(mx2, ok2 ? __uint_as_float(v1[e]) : -INFINITY);
-                            mx3 = fmaxf(mx3, ok3 ? __uint_as_float(v1[e + 1]) : -INFINITY);
-                        }
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 32; e += 2) {
-                            mx0 = fmaxf(mx0, __uint_as_float(v0[e]));
-                            mx1 = fmaxf(mx1, __uint_as_float(v0[e + 1]));
-                            mx2 = fmaxf(mx2, __uint_as_float(v1[e]));
-                            mx3 = fmaxf(mx3, __uint_as_float(v1[e + 1]));
-                        }
-                    }
-                }
-                m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-                if (need_mask && row_empty) m_tile = -INFINITY;
-            }
-            m_tile *= sl2;  // sl2 > 0: max commutes with the scale
-            const float m_new = fmaxf(m_ref, m_tile);
-            float alpha = 1.f;
-            if (t > 0) {
-                const bool grow = (m_new - m_ref) > 8.0f;  // also true when m_ref == -inf and m_new finite
-                if (__any_sync(0xffffffffu, grow)) {       // warp-uniform: the TMEM accesses below are .sync.aligned
-                    // O_g is about to be rewritten: P_g(t-1) V has retired -- S_g(t), whose completion this thread has just
-                    // waited for, was issued after it and tcgen05.mma retires in issue order (see the MMA warp)
-                    if (grow) {
-                        alpha = (m_ref == -INFINITY) ? 0.f : exp2f(m_ref - m_new);
-                        m_ref = m_new;
-                    }
-#pragma unroll 1
-                    for (int c = 0; c < D / 32; ++c) {
-                        uint32_t o[32];
-                        tmem_ld32(o_col + c * 32, o);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
-                        tmem_st32(o_col + c * 32, o);
-                    }
-                    tmem_st_wait();
-                }
-            } else {
-                m_ref = m_new;
-            }
-            const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
-            // ---- pass 2: p = 2^(s*scale - m) -> bf16 pairs written back IN PLACE over the already-read part of the S row
-            //      (P chunk c lands in columns [16c, 16c+16), all inside S columns [0, 32(c+1)) which this thread has read)
-            float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-            auto pass2 = [&](auto masked_tag) {
-                constexpr bool MASKED = decltype(masked_tag)::value;
-#pragma unroll 1
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t v[32];
-                    tmem_ld32(s_col + c * 32, v);
-                    tmem_ld_wait();
-                    uint32_t pk[16];
+                if (need_mask) {
 #pragma unroll
                     for (int e = 0; e < 32; e += 2) {
-                        float p0 = a2_exp2(fmaf(__uint_as_float(v[e]), sl2, neg_m));
-                        float p1 = a2_exp2(fmaf(__uint_as_float(v[e + 1]), sl2, neg_m));
+                        const bool ok0 = static_cast<uint32_t>(cbase + e - vlo) <= vspan;
+                        const bool ok1 = static_cast<uint32_t>(cbase + e + 1 - vlo) <= vspan;
+                        const bool ok2 = static_cast<uint32_t>(cbase + 32 + e - vlo) <= vspan;
+                        const bool ok3 = static_cast<uint32_t>(cbase + 33 + e - vlo) <= vspan;
+                        mx0 = fmaxf(mx0, ok0 ? __uint_as_float(s0[e]) : -INFINITY);
+                        mx1 = fmaxf(mx1, ok1 ? __uint_as_float(s0[e + 1]) : -INFINITY);
+                        mx2 = fmaxf(mx2, ok2 ? __uint_as_float(s1[e]) : -INFINITY);
+                        mx3 = fmaxf(mx3, ok3 ? __uint_as_float(s1[e + 1]) : -INFINITY);
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; e += 2) {
+                        mx0 = fmaxf(mx0, __uint_as_float(s0[e]));
+                        mx1 = fmaxf(mx1, __uint_as_float(s0[e + 1]));
+                        mx2 = fmaxf(mx2, __uint_as_float(s1[e]));
+                        mx3 = fmaxf(mx3, __uint_as_float(s1[e + 1]));
+                    }
+                }
+                float m_part = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+                if (need_mask && row_empty) m_part = -INFINITY;
+                // exchange the half-row maxima (buffer by tile parity).  After this barrier BOTH threads of the row have their
+                // scores in registers, so either may overwrite any column of the S row with P.
+                xg[(t & 1) * 256 + half * 128 + row] = m_part;
+                if (g == 0)
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                else
+                    asm volatile("bar.sync 2, 256;" ::: "memory");
+                float m_tile = fmaxf(m_part, xg[(t & 1) * 256 + (half ^ 1) * 128 + row]) * sl2;
+                const float m_new = fmaxf(m_ref, m_tile);
+                float alpha = 1.f;
+                if (t > 0) {
+                    const bool grow = (m_new - m_ref) > 8.0f;
+                    if (__any_sync(0xffffffffu, grow)) {   // both threads of a row decide alike (same m_new, m_ref)
+                        if (grow) {
+                            alpha = (m_ref == -INFINITY) ? 0.f : exp2f(m_ref - m_new);
+                            m_ref = m_new;
+                        }
+#pragma unroll 1
+                        for (int c = 0; c < OC / 32; ++c) {
+                            uint32_t o[32];
+                            tmem_ld32(o_col + c * 32, o);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+                            tmem_st32(o_col + c * 32, o);
+                        }
+                        tmem_st_wait();
+                    }
+                } else {
+                    m_ref = m_new;
+                }
+                const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
+                float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+                auto exp_pack = [&](auto masked_tag, const uint32_t (&sv)[32], int col0, uint32_t (&pk)[16]) {
+                    constexpr bool MASKED = decltype(masked_tag)::value;
+#pragma unroll
+                    for (int e = 0; e < 32; e += 2) {
+                        float p0 = a2_exp2(fmaf(__uint_as_float(sv[e]), sl2, neg_m));
+                        float p1 = a2_exp2(fmaf(__uint_as_float(sv[e + 1]), sl2, neg_m));
                         if (MASKED) {
-                            p0 = (static_cast<uint32_t>(c * 32 + e - vlo) <= vspan && !row_empty) ? p0 : 0.f;
-                            p1 = (static_cast<uint32_t>(c * 32 + e + 1 - vlo) <= vspan && !row_empty) ? p1 : 0.f;
+                            p0 = (static_cast<uint32_t>(col0 + e - vlo) <= vspan && !row_empty) ? p0 : 0.f;
+                            p1 = (static_cast<uint32_t>(col0 + e + 1 - vlo) <= vspan && !row_empty) ? p1 : 0.f;
                         }
                         if (e & 2) {
                             l2 += p0;
@@ -330,46 +333,220 @@ attention2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                         }
                         pk[e >> 1] = pack_bf16x2(p0, p1);
                     }
-                    tmem_st16(s_col + c * 16, pk);
-                }
-            };
-            if (need_mask)
-                pass2(std::true_type{});
-            else
-                pass2(std::false_type{});
-            l_run = l_run * alpha + ((l0 + l1) + (l2 + l3));
-            tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(&p_full[g]);
-        }
-
-        // ---- epilogue: O / l -> bf16 -> global (one row per thread)
-        if (n_g > 0) {
-            mbar_wait(&o_full[g], 0);
-            tc_fence_after();
-        }
-        const bool live = (g == 0) || activeB;
-        const float inv_l = (l_run > 0.f) ? 1.0f / l_run : 0.f;
-        bf16* orow = a.out + (static_cast<size_t>(b) * a.Tq + qi) * a.ldo + h * D;
-#pragma unroll 1
-        for (int c = 0; c < D / 32; ++c) {
-            uint32_t o[32];
-            if (n_g > 0) {
-                tmem_ld32(o_col + c * 32, o);
-                tmem_ld_wait();
-            } else {
-#pragma unroll
-                for (int e = 0; e < 32; ++e) o[e] = 0u;
+                };
+                uint32_t pk[16];
+                // P columns [half * 32, half * 32 + 32): keys cbase .. cbase + 63, two per 32-bit cell
+                if (need_mask)
+                    exp_pack(std::true_type{}, s0, cbase, pk);
+                else
+                    exp_pack(std::false_type{}, s0, cbase, pk);
+                tmem_st16(s_col + half * 32, pk);
+                if (need_mask)
+                    exp_pack(std::true_type{}, s1, cbase + 32, pk);
+                else
+                    exp_pack(std::false_type{}, s1, cbase + 32, pk);
+                tmem_st16(s_col + half * 32 + 16, pk);
+                l_run = l_run * alpha + ((l0 + l1) + (l2 + l3));
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(&p_full[g]);
             }
-            if (live && qi < a.Tq) {
+
+            // ---- epilogue: the two threads of a row add their partial sums and split the D output columns
+            if (n_g > 0) {
+                mbar_wait(&o_full[g], 0);
+                tc_fence_after();
+            }
+            xg[512 + half * 128 + row] = l_run;
+            if (g == 0)
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            else
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+            const float l_tot = l_run + xg[512 + (half ^ 1) * 128 + row];
+            const bool live = (g == 0) || activeB;
+            const float inv_l = (l_tot > 0.f) ? 1.0f / l_tot : 0.f;
+            bf16* orow = a.out + (static_cast<size_t>(b) * a.Tq + qi) * a.ldo + h * D + half * OC;
+#pragma unroll 1
+            for (int c = 0; c < OC / 32; ++c) {
+                uint32_t o[32];
+                if (n_g > 0) {
+                    tmem_ld32(o_col + c * 32, o);
+                    tmem_ld_wait();
+                } else {
 #pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) {
-                    const uint4 pk = make_uint4(
-                        pack_bf16x2(__uint_as_float(o[8 * q4]) * inv_l, __uint_as_float(o[8 * q4 + 1]) * inv_l),
-                        pack_bf16x2(__uint_as_float(o[8 * q4 + 2]) * inv_l, __uint_as_float(o[8 * q4 + 3]) * inv_l),
-                        pack_bf16x2(__uint_as_float(o[8 * q4 + 4]) * inv_l, __uint_as_float(o[8 * q4 + 5]) * inv_l),
-                        pack_bf16x2(__uint_as_float(o[8 * q4 + 6]) * inv_l, __uint_as_float(o[8 * q4 + 7]) * inv_l));
-                    reinterpret_cast<uint4*>(orow + c * 32)[q4] = pk;
+                    for (int e = 0; e < 32; ++e) o[e] = 0u;
+                }
+                if (live && qi < a.Tq) {
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        const uint4 pk4 = make_uint4(
+                            pack_bf16x2(__uint_as_float(o[8 * q4]) * inv_l, __uint_as_float(o[8 * q4 + 1]) * inv_l),
+                            pack_bf16x2(__uint_as_float(o[8 * q4 + 2]) * inv_l, __uint_as_float(o[8 * q4 + 3]) * inv_l),
+                            pack_bf16x2(__uint_as_float(o[8 * q4 + 4]) * inv_l, __uint_as_float(o[8 * q4 + 5]) * inv_l),
+                            pack_bf16x2(__uint_as_float(o[8 * q4 + 6]) * inv_l, __uint_as_float(o[8 * q4 + 7]) * inv_l));
+                        reinterpret_cast<uint4*>(orow + c * 32)[q4] = pk4;
+                    }
+                }
+            }
+        } else {
+        // ---- softmax: group g = Q tile g, one thread per query row (= TMEM lane)
+            const int g = (warp - 2) >> 2;
+            const int qd = warp & 3;               // TMEM lane quarter this warp may touch
+            const int row = qd * 32 + lane;
+            const int q0g = q0 + g * A2_BM;
+            const int qi = q0g + row;
+            const int n_g = g ? nB : nA;
+            const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
+            const uint32_t s_col = tmem_S0 + g * A2_BN + lane_off;
+            const uint32_t o_col = tmem_O0 + g * D + lane_off;
+            const int kvl = a.kv_len ? min(a.kv_len[b], a.Tk) : a.Tk;
+            const int kvs = a.kv_start ? a.kv_start[b] : 0;
+            const int causal_hi = a.causal ? qi + (a.Tk - a.Tq) : 0x7fffffff;  // last visible key (inclusive)
+            const float sl2 = a.scale_log2;
+            float m_ref = -INFINITY, l_run = 0.f;
+    
+            for (int t = 0; t < n_g; ++t) {
+                const int k0 = (j_lo + t) * A2_BN;
+                mbar_wait(&s_full[g], t & 1);
+                tc_fence_after();
+                const bool need_mask = (k0 < kvs) || (k0 + A2_BN > kvl) || (a.causal && k0 + A2_BN - 1 > q0g + (a.Tk - a.Tq));
+                const int vlo = max(kvs - k0, 0);
+                const int vhi = min(min(kvl - 1, causal_hi) - k0, A2_BN - 1);
+                const uint32_t vspan = static_cast<uint32_t>(vhi - vlo);
+                const bool row_empty = vhi < vlo;
+                // ---- pass 1: row max (thread-local)
+                float m_tile;
+                {
+                    float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+                    // not unrolled over the column chunks: the fully unrolled kernel was 64 KB of SASS and the softmax warps spent 19 %
+                    // of their non-waiting samples on instruction-cache misses (stall_no_inst, profiles/r02c_ncu_attention_v2.md)
+    #pragma unroll 1
+                    for (int c = 0; c < 4; c += 2) {
+                        uint32_t v0[32], v1[32];
+                        tmem_ld32(s_col + c * 32, v0);
+                        tmem_ld32(s_col + c * 32 + 32, v1);
+                        tmem_ld_wait();
+                        if (need_mask) {
+    #pragma unroll
+                            for (int e = 0; e < 32; e += 2) {
+                                const bool ok0 = static_cast<uint32_t>(c * 32 + e - vlo) <= vspan;
+                                const bool ok1 = static_cast<uint32_t>(c * 32 + e + 1 - vlo) <= vspan;
+                                const bool ok2 = static_cast<uint32_t>(c * 32 + 32 + e - vlo) <= vspan;
+                                const bool ok3 = static_cast<uint32_t>(c * 32 + 33 + e - vlo) <= vspan;
+                                mx0 = fmaxf(mx0, ok0 ? __uint_as_float(v0[e]) : -INFINITY);
+                                mx1 = fmaxf(mx1, ok1 ? __uint_as_float(v0[e + 1]) : -INFINITY);
+                                mx2 = fmaxf(mx2, ok2 ? __uint_as_float(v1[e]) : -INFINITY);
+                                mx3 = fmaxf(mx3, ok3 ? __uint_as_float(v1[e + 1]) : -INFINITY);
+                            }
+                        } else {
+    #pragma unroll
+                            for (int e = 0; e < 32; e += 2) {
+                                mx0 = fmaxf(mx0, __uint_as_float(v0[e]));
+                                mx1 = fmaxf(mx1, __uint_as_float(v0[e + 1]));
+                                mx2 = fmaxf(mx2, __uint_as_float(v1[e]));
+                                mx3 = fmaxf(mx3, __uint_as_float(v1[e + 1]));
+                            }
+                        }
+                    }
+                    m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+                    if (need_mask && row_empty) m_tile = -INFINITY;
+                }
+                m_tile *= sl2;  // sl2 > 0: max commutes with the scale
+                const float m_new = fmaxf(m_ref, m_tile);
+                float alpha = 1.f;
+                if (t > 0) {
+                    const bool grow = (m_new - m_ref) > 8.0f;  // also true when m_ref == -inf and m_new finite
+                    if (__any_sync(0xffffffffu, grow)) {       // warp-uniform: the TMEM accesses below are .sync.aligned
+                        // O_g is about to be rewritten: P_g(t-1) V has retired -- S_g(t), whose completion this thread has just
+                        // waited for, was issued after it and tcgen05.mma retires in issue order (see the MMA warp)
+                        if (grow) {
+                            alpha = (m_ref == -INFINITY) ? 0.f : exp2f(m_ref - m_new);
+                            m_ref = m_new;
+                        }
+    #pragma unroll 1
+                        for (int c = 0; c < D / 32; ++c) {
+                            uint32_t o[32];
+                            tmem_ld32(o_col + c * 32, o);
+                            tmem_ld_wait();
+    #pragma unroll
+                            for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+                            tmem_st32(o_col + c * 32, o);
+                        }
+                        tmem_st_wait();
+                    }
+                } else {
+                    m_ref = m_new;
+                }
+                const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
+                // ---- pass 2: p = 2^(s*scale - m) -> bf16 pairs written back IN PLACE over the already-read part of the S row
+                //      (P chunk c lands in columns [16c, 16c+16), all inside S columns [0, 32(c+1)) which this thread has read)
+                float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+                auto pass2 = [&](auto masked_tag) {
+                    constexpr bool MASKED = decltype(masked_tag)::value;
+    #pragma unroll 1
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t v[32];
+                        tmem_ld32(s_col + c * 32, v);
+                        tmem_ld_wait();
+                        uint32_t pk[16];
+    #pragma unroll
+                        for (int e = 0; e < 32; e += 2) {
+                            float p0 = a2_exp2(fmaf(__uint_as_float(v[e]), sl2, neg_m));
+                            float p1 = a2_exp2(fmaf(__uint_as_float(v[e + 1]), sl2, neg_m));
+                            if (MASKED) {
+                                p0 = (static_cast<uint32_t>(c * 32 + e - vlo) <= vspan && !row_empty) ? p0 : 0.f;
+                                p1 = (static_cast<uint32_t>(c * 32 + e + 1 - vlo) <= vspan && !row_empty) ? p1 : 0.f;
+                            }
+                            if (e & 2) {
+                                l2 += p0;
+                                l3 += p1;
+                            } else {
+                                l0 += p0;
+                                l1 += p1;
+                            }
+                            pk[e >> 1] = pack_bf16x2(p0, p1);
+                        }
+                        tmem_st16(s_col + c * 16, pk);
+                    }
+                };
+                if (need_mask)
+                    pass2(std::true_type{});
+                else
+                    pass2(std::false_type{});
+                l_run = l_run * alpha + ((l0 + l1) + (l2 + l3));
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(&p_full[g]);
+            }
+    
+            // ---- epilogue: O / l -> bf16 -> global (one row per thread)
+            if (n_g > 0) {
+                mbar_wait(&o_full[g], 0);
+                tc_fence_after();
+            }
+            const bool live = (g == 0) || activeB;
+            const float inv_l = (l_run > 0.f) ? 1.0f / l_run : 0.f;
+            bf16* orow = a.out + (static_cast<size_t>(b) * a.Tq + qi) * a.ldo + h * D;
+    #pragma unroll 1
+            for (int c = 0; c < D / 32; ++c) {
+                uint32_t o[32];
+                if (n_g > 0) {
+                    tmem_ld32(o_col + c * 32, o);
+                    tmem_ld_wait();
+                } else {
+    #pragma unroll
+                    for (int e = 0; e < 32; ++e) o[e] = 0u;
+                }
+                if (live && qi < a.Tq) {
+    #pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        const uint4 pk = make_uint4(
+                            pack_bf16x2(__uint_as_float(o[8 * q4]) * inv_l, __uint_as_float(o[8 * q4 + 1]) * inv_l),
+                            pack_bf16x2(__uint_as_float(o[8 * q4 + 2]) * inv_l, __uint_as_float(o[8 * q4 + 3]) * inv_l),
+                            pack_bf16x2(__uint_as_float(o[8 * q4 + 4]) * inv_l, __uint_as_float(o[8 * q4 + 5]) * inv_l),
+                            pack_bf16x2(__uint_as_float(o[8 * q4 + 6]) * inv_l, __uint_as_float(o[8 * q4 + 7]) * inv_l));
+                        reinterpret_cast<uint4*>(orow + c * 32)[q4] = pk;
+                    }
                 }
             }
         }
@@ -380,17 +557,17 @@ attention2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
-template <int D>
+template <int D, int TPR>
 static int launch_attention2(cudaStream_t stream, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
                              const Attn2Args& a, int B) {
     using Cfg = Attn2Cfg<D>;
-    auto kern = attention2_kernel<D>;
+    auto kern = attention2_kernel<D, TPR>;
     static DeviceOnce once;
     if (once.first()) {
         AF3_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     }
     dim3 grid(ceil_div(a.Tq, 2 * A2_BM), a.H, B);
-    kern<<<grid, 320, Cfg::SMEM_BYTES, stream>>>(mq, mk, mv, a);
+    kern<<<grid, 64 + 256 * TPR, Cfg::SMEM_BYTES, stream>>>(mq, mk, mv, a);
     AF3_CHECK_LAUNCH();
     return 0;
 }
@@ -420,8 +597,13 @@ int attention_v2(cudaStream_t stream, const bf16* q, int ldq, const bf16* k, con
         if (int e = make_tmap_3d(&mk, k, (uint64_t)Hkv * D, Tk, B, ldk, (uint64_t)Tk * ldk, 64, A2_BN, 1)) return e;
         if (int e = make_tmap_3d(&mv, v, (uint64_t)Hkv * D, Tk, B, ldk, (uint64_t)Tk * ldk, 64, A2_BN, 1)) return e;
     }
-    if (D == 64) return launch_attention2<64>(stream, mq, mk, mv, a, B);
-    return launch_attention2<128>(stream, mq, mk, mv, a, B);
+    // softmax threads per query row (see the kernel).  One per row is the default: the two-per-row variant (AF3_ATTN_TPR=2) is
+    // parity-clean but measured 7-12 % slower (profiles/r02i_microbench_attention.json: 96 registers with spills at 18 warps, one
+    // more named barrier per tile)
+    const char* e = getenv("AF3_ATTN_TPR");
+    const bool one = !(e && e[0] == '2');
+    if (D == 64) return one ? launch_attention2<64, 1>(stream, mq, mk, mv, a, B) : launch_attention2<64, 2>(stream, mq, mk, mv, a, B);
+    return one ? launch_attention2<128, 1>(stream, mq, mk, mv, a, B) : launch_attention2<128, 2>(stream, mq, mk, mv, a, B);
 }
 
 }  // namespace af3

@@ -91,8 +91,8 @@ struct GemmCfg {
     //   slices written by the peer CTAs through distributed shared memory (<= 18.5 KB for 2..8 splits)
     static constexpr int ZONE_BYTES = (SWAP && NA == 1) ? 19456 : 0;
     static constexpr int EPI_STAGE_BYTES = (SWAP ? 32 * 128 * 2 : 4 * 2 * 4096) + ZONE_BYTES;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers: (3 STAGES + 12) x 8 B + slot*/;
-    static_assert((3 * STAGES + 12) * 8 + 16 <= 512, "barrier area");
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers: (4 STAGES + 12) x 8 B + slot*/;
+    static_assert((4 * STAGES + 12) * 8 + 16 <= 512, "barrier area");
     static_assert(2 * ACC_COLS <= 512, "TMEM budget");
     static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
 };
@@ -141,7 +141,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
     uint64_t* tempty = tfull + 2;
     uint64_t* rbar = tempty + 2;  // [4 warps][2 buffers] residual-tile arrival
     uint64_t* xf = rbar + 8;      // [STAGES] activation tile normalised in place (fused RMSNorm, swap mode)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xf + STAGES);
+    uint64_t* xfull = xf + STAGES;  // [STAGES] fused RMSNorm: the ACTIVATION tile of a stage has landed (its weights complete full[])
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xfull + STAGES);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -159,7 +160,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
             mbar_init(&tempty[i], 32 * EW);
         }
         for (int i = 0; i < 8; ++i) mbar_init(&rbar[i], 1);
-        for (int i = 0; i < STAGES; ++i) mbar_init(&xf[i], 1);
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&xf[i], 1);
+            mbar_init(&xfull[i], 1);
+        }
         if (a.tma_epi) {
             tma_prefetch_desc(&map_out);
             if ((((EPI >= 0) ? EPI : a.flags) & EPI_RESID) && a.res_period == 0) tma_prefetch_desc(&map_res);
@@ -201,7 +205,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
                     tile_coords(t0 / k_splits, a, r, c);
                     const int sp = t0 % k_splits;
                     for (int kb = kb_lo(sp); kb < kb_lo(sp + 1) && prefetched < STAGES; ++kb, ++prefetched) {
-                        mbar_arrive_expect_tx(&full[prefetched], Cfg::STAGE_BYTES);
+                        // fused RMSNorm: the activation tile completes its own barrier (xfull), so that it can be normalised while
+                        // the 8 x larger weight tile is still in flight -- a stage must not sit "landed but waiting for the
+                        // transform": with ~216 KB in flight per SM the streams are latency-bound on ring depth
+                        mbar_arrive_expect_tx(&full[prefetched], a.norm_w ? Cfg::R_BYTES : Cfg::STAGE_BYTES);
                         uint8_t* sR = smem + prefetched * Cfg::STAGE_BYTES;
 #pragma unroll
                         for (int na = 0; na < NA; ++na)
@@ -219,9 +226,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
                 for (int kb = kb_lo(sp); kb < kb_lo(sp + 1); ++kb, ++issued) {
                     uint8_t* sR = smem + stage * Cfg::STAGE_BYTES;
                     uint8_t* sC = sR + Cfg::R_BYTES;
+                    [[maybe_unused]] const bool split_x = SWAP && a.norm_w;
                     if (issued >= prefetched) {
                         mbar_wait(&empty[stage], phase ^ 1);
-                        mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+                        mbar_arrive_expect_tx(&full[stage], split_x ? Cfg::R_BYTES : Cfg::STAGE_BYTES);
 #pragma unroll
                         for (int na = 0; na < NA; ++na)
                             tma_load_2d(sR + na * 128 * BK * 2, &map_r, &full[stage], kb * BK,
@@ -230,6 +238,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
                     if (!SWAP && a.swiglu_up_row0) {   // [gate; up] rows: two 128-row boxes make up the 256-column tile
                         tma_load_2d(sC, &map_c, &full[stage], kb * BK, c * 128);
                         tma_load_2d(sC + 128 * BK * 2, &map_c, &full[stage], kb * BK, a.swiglu_up_row0 + c * 128);
+                    } else if (split_x) {
+                        mbar_arrive_expect_tx(&xfull[stage], Cfg::C_BYTES);
+                        tma_load_2d(sC, &map_c, &xfull[stage], kb * BK, c * BN);
                     } else {
                         tma_load_2d(sC, &map_c, &full[stage], kb * BK, c * BN);
                     }
@@ -342,14 +353,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
                     // Ring stage s is always rewritten by the same warp (s % 4): a parity wait on full[s] can only tell consecutive
                     // uses of a stage apart, so the warp that waits for use n must be the one that saw use n - 1.  (Assigning k blocks
                     // round-robin, i % 4, let a warp skip a use of a 6-deep ring and race two uses ahead: deadlock at K = 3584.)
-                    for (int i = 0; i < nkb; ++i) {
-                        const int kb = kb0 + i, stage = i % STAGES;
-                        if ((stage & 3) != ew) continue;
-                        const uint32_t phase = (i / STAGES) & 1;
-                        uint4 wq[8];
+                    // norm weights of the warp's FIRST block; inside the loop the next owned block's are requested before this block
+                    // is waited for (they are L2 hits ~0.7 us away; 128 B per block, the same address in every lane)
+                    auto next_owned = [&](int i) {
+                        for (++i; i < nkb; ++i)
+                            if (((i % STAGES) & 3) == ew) return i;
+                        return -1;
+                    };
+                    int i = (ew < STAGES && ew < nkb) ? ew : -1;   // stage of block i is i % STAGES = i for i < STAGES
+                    uint4 wq[8];
+                    if (i >= 0) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) wq[j] = __ldg(wv + kb * 8 + j);   // same address in every lane: one L1 transaction
-                        mbar_wait(&full[stage], phase);
+                        for (int j = 0; j < 8; ++j) wq[j] = __ldg(wv + (kb0 + i) * 8 + j);
+                    }
+                    const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
+                    while (i >= 0) {
+                        const int stage = i % STAGES;
+                        const uint32_t phase = (i / STAGES) & 1;
+                        const int inext = next_owned(i);
+                        uint4 wn[8];
+                        if (inext >= 0) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) wn[j] = __ldg(wv + (kb0 + inext) * 8 + j);
+                        }
+                        mbar_wait(&xfull[stage], phase);
                         uint8_t* sX = smem + stage * Cfg::STAGE_BYTES + Cfg::R_BYTES + lane * 128;   // this token's row of the tile
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
@@ -360,14 +387,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
                             uint32_t o[4];
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
-                                const float2 xf2 = __bfloat1622float2(xh[e]), wf = __bfloat1622float2(wh[e]);
-                                o[e] = pack_bf16x2(wf.x * bf16_round(xf2.x * rstd), wf.y * bf16_round(xf2.y * rstd));
+                                // bf16(x * rstd) in fp32 with one rounding, then w * (that): the product of two bf16 values rounded to
+                                // bf16 is what the packed HFMA2.BF16 computes (fp32 product, one rounding) -- 3 instead of 8 instructions
+                                // per element
+                                const float2 xf2 = __bfloat1622float2(xh[e]);
+                                const __nv_bfloat162 xn = __floats2bfloat162_rn(xf2.x * rstd, xf2.y * rstd);
+                                const __nv_bfloat162 y = __hfma2(wh[e], xn, zero2);
+                                o[e] = *reinterpret_cast<const uint32_t*>(&y);
                             }
                             *px = make_uint4(o[0], o[1], o[2], o[3]);
                         }
                         fence_proxy_async_smem();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&xf[stage]);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) wq[j] = wn[j];
+                        i = inext;
                     }
                 }
             }

@@ -353,11 +353,12 @@ class Qwen2ForCausalLM(nn.Module):
         pos0 = cache.length
         rope_cs = None
         fused_qkv = decode and B <= 64  # few-token ("swapped") GEMM with RoPE + KV append in its epilogue
-        # Decode step: RMSNorm fused ACROSS the GEMMs (include/af3b200.h af3_gemm_fusion).  The residual GEMMs (o, down) emit the
-        # per-row-tile sums of squares of the rows they store; the next q/k/v / gate-up GEMM normalises its activation tiles in
-        # shared memory.  55 of the 57 norm launches of a step (and two dependency hops each) disappear; only layer 0's input
-        # norm (input from the embedding gather) and the final norm stay kernels.  AF3_FUSE_NORM=0: the round-1 chain (A/B runs).
-        fuse_norm = fused_qkv and self.hid % 64 == 0 and self.hid <= 4096 and os.environ.get("AF3_FUSE_NORM", "1") != "0"
+        # Decode step with RMSNorm fused ACROSS the GEMMs (include/af3b200.h af3_gemm_fusion): the residual GEMMs (o, down) emit the
+        # per-row-tile sums of squares of the rows they store, the next q/k/v / gate-up GEMM normalises its activation tiles in shared
+        # memory; 55 of the 57 norm launches of a step disappear.  OPT-IN (AF3_FUSE_NORM=1): parity-clean, but measured 3-7 % SLOWER
+        # than the chain with stand-alone norm kernels in four A/B runs (profiles/r02g..i_decode_timeline_*): the few-token streams
+        # are latency-bound on ring depth, and a stage that waits for its activation tile to be rewritten is a stage not in flight.
+        fuse_norm = fused_qkv and self.hid % 64 == 0 and self.hid <= 4096 and os.environ.get("AF3_FUSE_NORM", "0") == "1"
         n_parts = -(-self.hid // 128)
         if fused_qkv:
             rope_cs = ops.rope_table(B, D, cache.pos_dev, cache.kv_start, self._inv_freq)
@@ -745,7 +746,7 @@ class AudioFlamingo3ForConditionalGeneration(nn.Module):
             Tmax = AF3KVCache.bucket(S + max_new_tokens)
             # the captured graph holds raw addresses: key it on the weight storages too, so a re-pack (load_reference_state_dict) or
             # a move (.to()) can never leave a stale graph replaying against freed memory
-            key = (B, Tmax, use_graph, os.environ.get("AF3_PDL", "1") != "0", os.environ.get("AF3_FUSE_NORM", "1") != "0", str(dev),
+            key = (B, Tmax, use_graph, os.environ.get("AF3_PDL", "1") != "0", os.environ.get("AF3_FUSE_NORM", "0") == "1", str(dev),
                    lm.lm_head.weight.data_ptr(), lm._packed[0][0].data_ptr(), lm._packed[-1][2].data_ptr())
             st = self._decode_state
             if st is not None and st["key"] == key:

@@ -1,4 +1,5 @@
-"""Prefill / encoder attention at the bench's shapes, round-1 kernel (AF3_ATTN_V1=1) vs round-2 kernel (default):
+"""Prefill / encoder attention at the bench's shapes, round-1 kernel (AF3_ATTN_V1=1) vs round-2 kernel with one (default) or two
+(AF3_ATTN_TPR=2) softmax threads per query row:
    encoder: 32 windows x 20 heads x 64, 1500 frames, bidirectional (fused q/k/v buffer, as the tower calls it)
    prefill: 32 sequences x 28:4 GQA x 128, 780 tokens, causal over the KV cache
 CUDA events around 20 back-to-back launches after 3 warm-ups; FLOPs = 4 Tq Tk D per (batch, head), halved when causal (the useful
@@ -56,8 +57,9 @@ for name, mk in (("encoder_d64_t1500", encoder), ("prefill_d128_t780_causal", pr
     fn, flops, out = mk()
     row = {}
     outs = {}
-    for impl in ("v1", "v2") if not only_impl else (only_impl,):
+    for impl in ("v1", "v2_tpr2", "v2") if not only_impl else (only_impl,):
         os.environ["AF3_ATTN_V1"] = "1" if impl == "v1" else "0"
+        os.environ["AF3_ATTN_TPR"] = "2" if impl == "v2_tpr2" else "1"
         ms = timed(fn)
         row[impl] = {"ms": round(ms, 4), "tflops": round(flops / ms / 1e9, 1)}
         outs[impl] = out.float().clone()

@@ -114,8 +114,9 @@ def sdpa(q, k, v, scale, mask):
     return torch.nan_to_num(torch.softmax(s, -1), nan=0.0) @ v
 
 
-for impl in ("0", "1"):
+for impl, tpr in (("0", "2"), ("0", "1"), ("1", "2")):
     os.environ["AF3_ATTN_V1"] = impl
+    os.environ["AF3_ATTN_TPR"] = tpr
     Bq, Hh, Dd, T = 2, 2, 64, 300
     qkv = rnd(Bq * T, 3 * Hh * Dd)
     out = torch.zeros((Bq, T, Hh * Dd), device=dev, dtype=bf16)
@@ -125,7 +126,7 @@ for impl in ("0", "1"):
     q, k, v = [t.float().view(Bq, T, Hh, Dd).transpose(1, 2) for t in qkv.split(Hh * Dd, dim=1)]
     m = torch.ones((Bq, 1, T, T), dtype=torch.bool, device=dev)
     m[1, :, :, 77:] = False
-    ok(f"attention bidirectional D=64 (AF3_ATTN_V1={impl})", out.view(Bq, T, Hh, Dd).transpose(1, 2), sdpa(q, k, v, 0.125, m))
+    ok(f"attention bidirectional D=64 (AF3_ATTN_V1={impl} TPR={tpr})", out.view(Bq, T, Hh, Dd).transpose(1, 2), sdpa(q, k, v, 0.125, m))
     H2, Hk2, D2, T2, Tm2 = 4, 2, 128, 300, 384
     qk2 = rnd(Bq * T2, (H2 + 2 * Hk2) * D2)
     kc, vc = torch.zeros((Bq, Hk2, Tm2, D2), device=dev, dtype=bf16), torch.zeros((Bq, Hk2, Tm2, D2), device=dev, dtype=bf16)
@@ -141,9 +142,10 @@ for impl in ("0", "1"):
     m[1, :, :, :130] = False
     ref = sdpa(q, kk.float().repeat_interleave(2, 1), vv.float().repeat_interleave(2, 1), D2 ** -0.5, m)
     got = o2.view(Bq, T2, H2, D2).transpose(1, 2)
-    ok(f"attention causal GQA D=128 (AF3_ATTN_V1={impl})", got[0], ref[0])
-    ok(f"attention causal GQA D=128 left-padded row (AF3_ATTN_V1={impl})", got[1, :, 130:], ref[1, :, 130:])
+    ok(f"attention causal GQA D=128 (AF3_ATTN_V1={impl} TPR={tpr})", got[0], ref[0])
+    ok(f"attention causal GQA D=128 left-padded row (AF3_ATTN_V1={impl} TPR={tpr})", got[1, :, 130:], ref[1, :, 130:])
 os.environ.pop("AF3_ATTN_V1")
+os.environ.pop("AF3_ATTN_TPR")
 
 for splits in ("1", "3"):
     os.environ["AF3_DECODE_SPLITS"] = splits

@@ -194,11 +194,13 @@ def _sdpa_ref(q, k, v, scale, mask):
     return p @ v
 
 
-@pytest.fixture(params=["v2", "v1"])
+@pytest.fixture(params=["v2", "v2_tpr2", "v1"])
 def attn_impl(request, monkeypatch):
-    """Both generations of the prefill / encoder attention kernel go through the same parity cases: v2 (two Q tiles per CTA,
-    P in tensor memory; the default) and the round-1 kernel (AF3_ATTN_V1=1, kept as its cross-check)."""
+    """All variants of the prefill / encoder attention kernel go through the same parity cases: v2 (two Q tiles per CTA, P in
+    tensor memory; one softmax thread per row = the default, two per row = AF3_ATTN_TPR=2) and the round-1 kernel
+    (AF3_ATTN_V1=1, kept as cross-check)."""
     monkeypatch.setenv("AF3_ATTN_V1", "1" if request.param == "v1" else "0")
+    monkeypatch.setenv("AF3_ATTN_TPR", "2" if request.param == "v2_tpr2" else "1")
     return request.param
 
 

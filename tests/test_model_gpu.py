@@ -306,7 +306,7 @@ def test_generate_reuses_decode_graph_across_calls(O):
 
 
 def test_fused_rmsnorm_decode_matches_unfused_chain(O, monkeypatch):
-    """AF3_FUSE_NORM=1 (RMSNorm fused across the decode step's GEMMs, the default) vs 0 (stand-alone norm kernels, round 1's chain):
+    """AF3_FUSE_NORM=1 (RMSNorm fused across the decode step's GEMMs; opt-in, measured slower) vs 0 (stand-alone norm kernels):
     same greedy ids; logits within bf16 noise of each other; CUDA-graph replay of the fused chain == its eager execution bit for bit."""
     from audio_flamingo_b200 import AudioFlamingo3ForConditionalGeneration
 
