@@ -622,7 +622,7 @@ def run_ours(args):
         "gpu_launches": launches,
         "audio_s_per_s": audio_s_per_s, "decode_tok_s": decode_tok_s, "stage_ms": stage_ms, "stage_ms_per_step": stage_ms_per_step, "host_decode_enqueue_ms": host_decode_enqueue_ms, "host_token_gaps": host_token_gaps, "host_cpu": host_cpu,
         "roofline": roofline, "roofline_prefill_gemm": roofline_prefill_gemm, "roofline_decode_step": decode_roofline,
-        "kernels": table[:16], "decode_step_kernel_ms": dec, "decode_step_us_in_graph_trace": trace_step_us,
+        "kernels": table[:32], "decode_step_kernel_ms": dec, "decode_step_us_in_graph_trace": trace_step_us,
         "gpu_reference": gpu_ref, "extras": extras,
         "cpu_baseline": cpu, "clocks": clocks,
     }
