@@ -20,7 +20,11 @@ def __getattr__(name):  # lazy: keep `import audio_flamingo_b200` light (torch/t
         from . import processing
 
         return getattr(processing, name)
-    if name in ("shard_rows", "gather_tokens"):
+    if name == "GatedCrossAttentionLayer":
+        from . import xattn
+
+        return xattn.GatedCrossAttentionLayer
+    if name in ("shard_rows", "gather_tokens", "plan_kv_capacity", "kv_bytes_per_token"):
         from . import sharding
 
         return getattr(sharding, name)

@@ -37,6 +37,7 @@ SIGNATURES = {
     "af3_rope_kv_append": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "af3_rotary_time_emb": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _f, _f]),
     "af3_rope_table": (_i, [_p, _p, _i, _i, _p, _p, _p]),
+    "af3_gated_residual": (_i, [_p, _p, _p, _p, _i, _p, _p, _i, _i]),
     "af3_gemm_qkv_rope": (_i, [_p, _p, _i, _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i, _p, _p, _sz, _p]),
     "af3_gemm_bf16_fused": (_i, [_p, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p, _sz, _p]),
     "af3_decode_attention": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _f]),

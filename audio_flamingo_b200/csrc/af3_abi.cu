@@ -25,6 +25,8 @@ int gemm_bf16(cudaStream_t stream, const bf16* x, int ldx, const bf16* w, int ld
               void* workspace, size_t workspace_bytes, const RopeEpilogue* rope, const NormFusion* nf);
 int rotary_time(cudaStream_t stream, bf16* x, const float* ts, const float* inv_freq, int W, int T, int dim, int n_freq,
                 float window_duration, float max_len);
+int gated_residual(cudaStream_t stream, const bf16* resid, const bf16* y, const bf16* alpha, int alpha_scalar, const int* row_gate,
+                   bf16* out, int rows, int dim);
 int rope_table(cudaStream_t stream, float* cs, int B, int D, const int* pos_dev, const int* kv_start, const float* inv_freq);
 size_t gemm_workspace_bytes();
 int trace_begin(void* buf, size_t bytes);
@@ -108,6 +110,11 @@ int af3_gemm_bf16_fused(void* stream, const void* x, int ldx, const void* w, int
 int af3_rotary_time_emb(void* stream, void* x, const float* timestamps, const float* inv_freq, int W, int T, int dim, int n_freq,
                         float window_duration, float max_len) {
     return af3::rotary_time(S(stream), B16M(x), timestamps, inv_freq, W, T, dim, n_freq, window_duration, max_len);
+}
+
+int af3_gated_residual(void* stream, const void* resid, const void* y, const void* alpha, int alpha_is_scalar, const int* row_gate,
+                       void* out, int rows, int dim) {
+    return af3::gated_residual(S(stream), B16(resid), B16(y), B16(alpha), alpha_is_scalar, row_gate, B16M(out), rows, dim);
 }
 
 int af3_rope_table(void* stream, float* cs, int B, int D, const int* pos_dev, const int* kv_start, const float* inv_freq) {

@@ -491,6 +491,46 @@ int rotary_time(cudaStream_t stream, bf16* x, const float* ts, const float* inv_
     return 0;
 }
 
+// Flamingo-style gated residual ([O] transformers/models/idefics/modeling_idefics.py:796-806, the executable analogue of AF2's
+// gated xattn-dense block):  out = resid + tanh(alpha) * y   with every bf16 op of the reference rounded:
+// t = bf16(tanh(alpha)), p = bf16(t * y), out = bf16(resid + p).  alpha: bf16 [dim] (alpha_type "vector") or one value
+// (alpha_scalar != 0, alpha_type "float").  row_gate (optional, int32 [rows]): rows whose gate is 0 take y = 0 (tokens that attend
+// to no media, idefics:797).  One warp per row, 16-byte accesses.
+__global__ void __launch_bounds__(256)
+gated_residual_kernel(const bf16* __restrict__ resid, const bf16* __restrict__ y, const bf16* __restrict__ alpha, int alpha_scalar,
+                      const int* __restrict__ row_gate, bf16* __restrict__ out, int rows, int dim) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const bool open = row_gate ? (row_gate[row] != 0) : true;
+    const uint4* rp = reinterpret_cast<const uint4*>(resid + static_cast<size_t>(row) * dim);
+    const uint4* yp = reinterpret_cast<const uint4*>(y + static_cast<size_t>(row) * dim);
+    uint4* op = reinterpret_cast<uint4*>(out + static_cast<size_t>(row) * dim);
+    const float t_scalar = alpha_scalar ? bf16_round(tanhf(__bfloat162float(alpha[0]))) : 0.f;
+    for (int c = lane; c < dim / 8; c += 32) {
+        float r[8], v[8], a8[8], o[8];
+        unpack8(rp[c], r);
+        unpack8(yp[c], v);
+        if (!alpha_scalar) unpack8(__ldg(reinterpret_cast<const uint4*>(alpha) + c), a8);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float t = alpha_scalar ? t_scalar : bf16_round(tanhf(a8[e]));
+            const float p = bf16_round(t * (open ? v[e] : 0.f));
+            o[e] = r[e] + p;
+        }
+        op[c] = pack8(o);
+    }
+}
+
+int gated_residual(cudaStream_t stream, const bf16* resid, const bf16* y, const bf16* alpha, int alpha_scalar, const int* row_gate,
+                   bf16* out, int rows, int dim) {
+    AF3_REQUIRE(dim % 8 == 0 && alpha, "gated_residual: dim must be a multiple of 8 and alpha given");
+    if (rows <= 0) return 0;
+    gated_residual_kernel<<<ceil_div(rows, 8), 256, 0, stream>>>(resid, y, alpha, alpha_scalar, row_gate, out, rows, dim);
+    AF3_CHECK_LAUNCH();
+    return 0;
+}
+
 // cos/sin table of ONE decode step for the RoPE-fused q/k/v projection epilogue: cs[b][i] = (bf16(cos), bf16(sin)) of
 // inv_freq[i] * position(b), position = slot - kv_start[b] (Q2M:100-113; identical for all layers of the step).
 __global__ void rope_table_kernel(float2* __restrict__ cs, int B, int half, const int* __restrict__ pos_dev,

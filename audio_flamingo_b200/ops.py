@@ -306,6 +306,22 @@ def rotary_time_emb(x, timestamps, inv_freq, W, T, window_duration, max_len):
     return x
 
 
+def gated_residual(resid, y, alpha, row_gate=None, out=None):
+    """out = resid + tanh(alpha) * y (Flamingo gate; alpha bf16 [dim] or 1 element); rows with row_gate == 0 take y = 0."""
+    lib = _lib.load()
+    _req(resid, bf16, "resid"), _req(y, bf16, "y"), _req(alpha, bf16, "alpha")
+    rows, dim = resid.shape
+    if out is None:
+        out = torch.empty_like(resid)
+    if row_gate is not None:
+        _req(row_gate, torch.int32, "row_gate")
+    with _Timed(("gated_residual", rows, dim, 0, 0)):
+        check(lib.af3_gated_residual(stream_ptr(), ptr(resid), ptr(y), ptr(alpha), int(alpha.numel() == 1), ptr(row_gate), ptr(out), rows, dim),
+              "af3_gated_residual")
+    _count(1)
+    return out
+
+
 def rope_table(B, D, pos_dev, kv_start, inv_freq, out=None):
     """(cos, sin) of this decode step for every sequence: fp32 [B, D/2, 2] (shared by all layers)."""
     lib = _lib.load()

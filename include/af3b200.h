@@ -124,6 +124,13 @@ int af3_rope_kv_append(void* stream, void* qkv, void* k_cache, void* v_cache, in
 int af3_rotary_time_emb(void* stream, void* x, const float* timestamps, const float* inv_freq, int W, int T, int dim,
                         int n_freq, float window_duration, float max_len);
 
+/* Flamingo-style gated residual, the element-wise half of a gated cross-attention / gated dense block (executable
+ * analogue [O] transformers/models/idefics/modeling_idefics.py:796-806): out = resid + tanh(alpha) * y with the reference's bf16
+ * rounding points.  alpha: bf16 [dim], or a single value when alpha_is_scalar.  row_gate (optional int32 [rows]): rows with gate 0
+ * take y = 0 (tokens that attend to no media).  out may alias resid. */
+int af3_gated_residual(void* stream, const void* resid, const void* y, const void* alpha, int alpha_is_scalar, const int* row_gate,
+                       void* out, int rows, int dim);
+
 /* Decode-step fusion of the q/k/v projection with RoPE and the KV append (Q2M:199-215 + CACHE:119-120 in one kernel):
  * out rows get the ROTATED query heads (columns [0, H*D)); rotated keys and the values go straight into the caches at
  * slot *pos_dev.  rope_cs [n_tok][D/2][2] fp32 from af3_rope_table (once per step, shared by all layers).

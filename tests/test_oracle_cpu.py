@@ -90,3 +90,24 @@ def test_length_arithmetic_matches_reference_formulae():
     assert per == [3, 1] and [len(c) for c in chunks] == [480000, 480000, 123456, 16000]
     frames = [(len(c) + 159) // 160 for c in chunks]
     assert tokens_per_sample(frames, per) == [sum(O.post_pool_len(f) for f in frames[:3]), O.post_pool_len(frames[3])]
+
+
+def test_af2_gated_xattn_restatement_matches_the_executable_analogue():
+    """AF2 itself is unpinned (no code in the container); the gated xattn-dense OPERATOR is pinned against the
+    executable analogue, transformers' IdeficsGatedCrossAttentionLayer, for vector and scalar gates, ragged media lengths and a
+    token that attends to no media."""
+    from oracle import af2_oracle as A
+
+    for alpha_type in ("vector", "float"):
+        layer = A.hf_gated_layer(seed=1, alpha_type=alpha_type)
+        B, T, Tm = 3, 11, 9
+        g = torch.Generator().manual_seed(2)
+        h = torch.randn(B, T, 512, generator=g)
+        m = torch.randn(B, Tm, 384, generator=g)
+        media_len = [9, 4, 1]
+        gate = torch.ones(B, T)
+        gate[2, 3] = 0
+        with torch.no_grad():
+            ref = layer(h, image_hidden_states=m, image_attention_mask=A.key_padding_mask(B, T, media_len, Tm), cross_attention_gate=gate)
+        ours = A.ref_gated_layer(layer.state_dict(), h, m, media_len, gate)
+        assert (ours - ref).abs().max().item() < 2e-5, alpha_type
