@@ -2,33 +2,15 @@
 #include "../../include/af3b200.h"
 
 #include "common.h"
+#include "gemm_epi.h"
 
 namespace af3 {
 const char* last_error_cstr();
-struct RopeEpilogue {
-    const float* cs;
-    bf16* k_cache;
-    bf16* v_cache;
-    const int* pos;
-    int H, Hkv, Tmax;
-};
-struct NormFusion {
-    const bf16* norm_w;
-    const float* norm_part;
-    int norm_parts, norm_ld;
-    float norm_eps;
-    float* sumsq_out;
-    int sumsq_ld;
-};
-int gemm_bf16(cudaStream_t stream, const bf16* x, int ldx, const bf16* w, int ldw, void* out, int ldo, int n_tok,
-              int n_feat, int K, int flags, const bf16* bias, const bf16* resid, int ld_res, int res_period,
-              void* workspace, size_t workspace_bytes, const RopeEpilogue* rope, const NormFusion* nf);
 int rotary_time(cudaStream_t stream, bf16* x, const float* ts, const float* inv_freq, int W, int T, int dim, int n_freq,
                 float window_duration, float max_len);
 int gated_residual(cudaStream_t stream, const bf16* resid, const bf16* y, const bf16* alpha, int alpha_scalar, const int* row_gate,
                    bf16* out, int rows, int dim);
 int rope_table(cudaStream_t stream, float* cs, int B, int D, const int* pos_dev, const int* kv_start, const float* inv_freq);
-size_t gemm_workspace_bytes();
 int trace_begin(void* buf, size_t bytes);
 int trace_end();
 int trace_seq();

@@ -17,14 +17,12 @@
 // transposed tile.  Tile order is grouped (GROUP_R row tiles share a col tile) so the 126 MB L2 holds the
 // working set of one wave and HBM sees each operand ~once.
 #include "common.h"
+#include "gemm_epi.h"
 #include "ptx.cuh"
 
 #include <cstdlib>
 
 namespace af3 {
-
-enum : int { EPI_BIAS = 1, EPI_GELU = 2, EPI_RESID = 4, EPI_SWIGLU = 8, EPI_F32OUT = 16, EPI_ROPE = 32,
-              EPI_SWIGLU_CONCAT = 64 /* host-side only: weight rows are [gate; up], not interleaved (stripped before dispatch) */ };
 
 struct GemmArgs {
     int R, C, K;  // extents of row operand, col operand, reduction
@@ -127,7 +125,11 @@ __device__ __forceinline__ float epi_swiglu(float g, float u) {
 // EW = epilogue warps (4 or 8).  With 8 (normal mode, epilogues without a TMA-prefetched residual) two warps share each
 // TMEM lane quarter and split the tile's 64-column groups between them: twice the issue slots for epilogue math, which
 // is what bounds short-K GEMMs with expensive epilogues (K = 1280 + GELU: erff per element).
-template <int BN, int NA, int STAGES, bool SWAP, int EPI, int EW>
+// EXP: the instantiation that carries the measured-slower experiments (fused RMSNorm consumer / producer, cluster split-K).  They
+// are compiled OUT of the default kernels: with them the few-token residual instantiation grew from 3648 to 7960 SASS instructions
+// and every q/k/v, o and down projection of the decode step lost ~3 us in its one-shot tail (cold instruction fetches on the critical
+// path: profiles/r02b_decode_timeline.md against r02h_decode_timeline_unfused.md, same code path, +300 us per step).
+template <int BN, int NA, int STAGES, bool SWAP, int EPI, int EW, bool EXP = false>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_c,
             const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res, const GemmArgs a) {
@@ -147,6 +149,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     if (threadIdx.x == 0) trace_mark(a.trace, 0);
+    // experiment switches: compile-time false (dead code) unless EXP
+    [[maybe_unused]] const bool x_norm = EXP && a.norm_w != nullptr;
+    [[maybe_unused]] const bool x_cluster = EXP && a.cluster_reduce != 0;
+    [[maybe_unused]] const bool x_sumsq = EXP && a.sumsq_out != nullptr;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_r);
@@ -182,7 +188,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
     if constexpr (SWAP && NA == 1) {
         // cluster split-K: phase 1 of the cluster barrier only says "this CTA is running" (a peer's shared memory may be written
         // once it is); everybody arrives here without blocking and waits right before its first remote store / at its end
-        if (a.cluster_reduce) cluster_arrive_relaxed();
+        if (x_cluster) cluster_arrive_relaxed();
     }
 
     const int k_splits = SWAP ? a.k_splits : 1;
@@ -208,7 +214,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
                         // fused RMSNorm: the activation tile completes its own barrier (xfull), so that it can be normalised while
                         // the 8 x larger weight tile is still in flight -- a stage must not sit "landed but waiting for the
                         // transform": with ~216 KB in flight per SM the streams are latency-bound on ring depth
-                        mbar_arrive_expect_tx(&full[prefetched], a.norm_w ? Cfg::R_BYTES : Cfg::STAGE_BYTES);
+                        mbar_arrive_expect_tx(&full[prefetched], x_norm ? Cfg::R_BYTES : Cfg::STAGE_BYTES);
                         uint8_t* sR = smem + prefetched * Cfg::STAGE_BYTES;
 #pragma unroll
                         for (int na = 0; na < NA; ++na)
@@ -226,7 +232,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
                 for (int kb = kb_lo(sp); kb < kb_lo(sp + 1); ++kb, ++issued) {
                     uint8_t* sR = smem + stage * Cfg::STAGE_BYTES;
                     uint8_t* sC = sR + Cfg::R_BYTES;
-                    [[maybe_unused]] const bool split_x = SWAP && a.norm_w;
+                    [[maybe_unused]] const bool split_x = SWAP && x_norm;
                     if (issued >= prefetched) {
                         mbar_wait(&empty[stage], phase ^ 1);
                         mbar_arrive_expect_tx(&full[stage], split_x ? Cfg::R_BYTES : Cfg::STAGE_BYTES);
@@ -253,7 +259,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
         }
         __syncwarp();
         if constexpr (SWAP && NA == 1) {
-            if (a.cluster_reduce) {   // every thread of the cluster takes part in both phases of the cluster barrier
+            if (x_cluster) {   // every thread of the cluster takes part in both phases of the cluster barrier
                 cluster_wait_acquire();
                 cluster_arrive_release();
                 cluster_wait_acquire();
@@ -275,7 +281,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full[stage], phase);
                     if constexpr (SWAP) {
-                        if (a.norm_w) mbar_wait(&xf[stage], phase);  // activation tile rewritten by the epilogue warps (fused RMSNorm)
+                        if (x_norm) mbar_wait(&xf[stage], phase);  // activation tile rewritten by the epilogue warps (fused RMSNorm)
                     }
                     tc_fence_after();
                     const uint32_t sR = smem_u32(smem + stage * Cfg::STAGE_BYTES);
@@ -304,7 +310,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
         }
         __syncwarp();
         if constexpr (SWAP && NA == 1) {
-            if (a.cluster_reduce) {
+            if (x_cluster) {
                 cluster_wait_acquire();
                 cluster_arrive_release();
                 cluster_wait_acquire();
@@ -317,8 +323,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
         const int flags = (EPI >= 0) ? EPI : a.flags;
         pdl_wait();  // residual reads / output writes / split-K workspace are ordered after every earlier kernel
         if (threadIdx.x == 64) trace_mark(a.trace, 1);
-        if constexpr (SWAP && EW == 4) {
-            if (a.norm_w) {
+        if constexpr (SWAP && EW == 4 && EXP) {
+            if (x_norm) {
                 // ---- fused RMSNorm of the activation tiles (this CTA's single work item).  WARP-granular: epilogue warp ew rewrites
                 //      the k blocks that land in ring stages ew, ew + 4, lane = token (128-byte row of the swizzled [32][64] tile), so up
                 //      to four tiles are in flight at once.  (The first version had all 128 threads walk the k blocks one after the other: at
@@ -672,7 +678,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
                     tmem_ld_wait();
                     [[maybe_unused]] int tok_lo = 0, tok_hi = 0x7fffffff;   // tokens this CTA finishes (cluster reduce: its slice)
                     if constexpr (NA == 1 && BN == 32) {
-                        if (k_splits > 1 && a.cluster_reduce) {
+                        if (k_splits > 1 && x_cluster) {
                             const int ks = k_splits, rank = t % k_splits;       // == %cluster_ctarank (consecutive CTAs form a cluster)
                             const int tokmax = (32 + ks - 1) / ks;
                             float* zone = reinterpret_cast<float*>(epi_stage + 32 * 128 * 2);   // [ks][tokmax][128]
@@ -843,7 +849,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
                                             yv = make_uint4(o4[0], o4[1], o4[2], o4[3]);
                                         }
                                         reinterpret_cast<uint4*>(op)[g4] = yv;
-                                        if (a.sumsq_out) {
+                                        if (x_sumsq) {
                                             const __nv_bfloat162* yh = reinterpret_cast<const __nv_bfloat162*>(&yv);
 #pragma unroll
                                             for (int e = 0; e < 4; ++e) {
@@ -854,7 +860,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
                                         }
                                     }
                                 }
-                                if (a.sumsq_out) {
+                                if (x_sumsq) {
                                     // the four lanes et % 4 = 0..3 hold the token's 4 x 32 features of this row tile (same warp, same
                                     // branch: tok is uniform over them); fixed order -> deterministic
                                     const unsigned grp = 0xFu << (lane & 28);
@@ -912,16 +918,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
     if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
-template <int BN, int NA, int STAGES, bool SWAP, int EPI, int EW = 4>
+template <int BN, int NA, int STAGES, bool SWAP, int EPI, int EW = 4, bool EXP = false>
 static int launch_epi(const CUtensorMap& mr, const CUtensorMap& mc, const CUtensorMap& mo, const CUtensorMap& mres,
                   const GemmArgs& a, cudaStream_t stream) {
     using Cfg = GemmCfg<BN, NA, STAGES, SWAP>;
-    auto kern = gemm_kernel<BN, NA, STAGES, SWAP, EPI, EW>;
+    auto kern = gemm_kernel<BN, NA, STAGES, SWAP, EPI, EW, EXP>;
     static DeviceOnce once;
     if (once.first()) {
         AF3_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     }
-    if constexpr (SWAP && NA == 1) {
+    if constexpr (SWAP && NA == 1 && EXP) {
         if (a.cluster_reduce && a.k_splits > 1) {
             // cluster split-K: the largest split count <= the requested one for which all tiles' clusters are co-resident
             // (a cluster needs k_splits free SMs inside ONE GPC; the answer is cached per device and cluster size)
@@ -968,8 +974,13 @@ static int launch_epi(const CUtensorMap& mr, const CUtensorMap& mc, const CUtens
 template <int BN, int NA, int STAGES, bool SWAP>
 static int launch(const CUtensorMap& mr, const CUtensorMap& mc, const CUtensorMap& mo, const CUtensorMap& mres,
                   const GemmArgs& a, cudaStream_t stream) {
-#define AF3_EPI_CASE(F) \
-    case (F):           \
+    // few-token kernels: the experiments (RMSNorm fusion, cluster split-K) live in their own instantiations
+    [[maybe_unused]] const bool exp = SWAP && (a.norm_w || a.sumsq_out || a.cluster_reduce);
+#define AF3_EPI_CASE(F)                                                                                      \
+    case (F):                                                                                                \
+        if constexpr (SWAP) {                                                                                \
+            if (exp) return launch_epi<BN, NA, STAGES, SWAP, (F), 4, true>(mr, mc, mo, mres, a, stream);     \
+        }                                                                                                    \
         return launch_epi<BN, NA, STAGES, SWAP, (F)>(mr, mc, mo, mres, a, stream);
     if constexpr (!SWAP) {
         // 8 epilogue warps where the epilogue (not the MMA) bounds the tile: TMA-store path without a TMA residual
@@ -1004,28 +1015,13 @@ static int launch(const CUtensorMap& mr, const CUtensorMap& mc, const CUtensorMa
         }
     }
 #undef AF3_EPI_CASE
+    if constexpr (SWAP) {
+        if (exp) return launch_epi<BN, NA, STAGES, SWAP, -1, 4, true>(mr, mc, mo, mres, a, stream);
+    }
     return launch_epi<BN, NA, STAGES, SWAP, -1>(mr, mc, mo, mres, a, stream);
 }
 
 size_t gemm_workspace_bytes() { return (8u << 20) + 4096 * sizeof(int); }
-
-struct RopeEpilogue {
-    const float* cs;
-    bf16* k_cache;
-    bf16* v_cache;
-    const int* pos;
-    int H, Hkv, Tmax;
-};
-
-// RMSNorm fusion across few-token GEMMs (see GemmArgs): consumer side (norm_w ...) and / or producer side (sumsq_out ...)
-struct NormFusion {
-    const bf16* norm_w;
-    const float* norm_part;
-    int norm_parts, norm_ld;
-    float norm_eps;
-    float* sumsq_out;
-    int sumsq_ld;
-};
 
 int gemm_bf16(cudaStream_t stream, const bf16* x, int ldx, const bf16* w, int ldw, void* out, int ldo, int n_tok,
               int n_feat, int K, int flags, const bf16* bias, const bf16* resid, int ld_res, int res_period,
@@ -1039,6 +1035,13 @@ int gemm_bf16(cudaStream_t stream, const bf16* x, int ldx, const bf16* w, int ld
     AF3_REQUIRE(!(flags & EPI_SWIGLU_CONCAT) || (swiglu && n_feat % 128 == 0), "gemm: the [gate; up] layout needs SwiGLU and n_feat % 128 == 0");
     flags &= ~EPI_SWIGLU_CONCAT;
     const int w_rows = swiglu ? 2 * ceil_div(n_feat, 128) * 128 : n_feat;
+    // short-K few-token projections (q/k/v, o of the decode step): one CTA per 32 weight rows over the full K, no split-K tail
+    if (n_tok <= 64 && !swiglu && !nf && gemm_skinny_applies(n_tok, n_feat, K, flags, ldx, ldw, ldo, ld_res, res_period, x, w, out, bias, resid)) {
+        if (flags & EPI_ROPE)
+            AF3_REQUIRE(rope && rope->cs && rope->k_cache && rope->v_cache && rope->pos && n_feat == (rope->H + 2 * rope->Hkv) * 128,
+                        "gemm: EPI_ROPE is the few-token fused q/k/v projection with head_dim 128");
+        return gemm_skinny(stream, x, ldx, w, ldw, reinterpret_cast<bf16*>(out), ldo, n_tok, n_feat, K, flags, bias, resid, ld_res, rope);
+    }
     GemmArgs a{};
     a.K = K;
     a.n_tok = n_tok;

@@ -746,8 +746,8 @@ class AudioFlamingo3ForConditionalGeneration(nn.Module):
             Tmax = AF3KVCache.bucket(S + max_new_tokens)
             # the captured graph holds raw addresses: key it on the weight storages too, so a re-pack (load_reference_state_dict) or
             # a move (.to()) can never leave a stale graph replaying against freed memory
-            key = (B, Tmax, use_graph, os.environ.get("AF3_PDL", "1") != "0", os.environ.get("AF3_FUSE_NORM", "0") == "1", str(dev),
-                   lm.lm_head.weight.data_ptr(), lm._packed[0][0].data_ptr(), lm._packed[-1][2].data_ptr())
+            key = (B, Tmax, use_graph, os.environ.get("AF3_PDL", "1") != "0", os.environ.get("AF3_FUSE_NORM", "0") == "1",
+                   os.environ.get("AF3_SKINNY_MAXK", ""), str(dev), lm.lm_head.weight.data_ptr(), lm._packed[0][0].data_ptr(), lm._packed[-1][2].data_ptr())
             st = self._decode_state
             if st is not None and st["key"] == key:
                 cache, step_fn = st["cache"], st["step"]       # same buffers -> the captured graph is valid as it stands

@@ -1,7 +1,7 @@
 """Single-kernel targets for `ncu --set full` at the bench's shapes (one warm-up launch, then two launches of the case):
     ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 1 -c 1 -o gpurun_out/X python profiles/ncu_targets.py prefill_gateup
 cases: prefill_gateup (24960 x 2*18944 x 3584, SwiGLU, token-major), prefill_down, decode_gateup (32 tokens), decode_down (split-K),
-       decode_qkv (split-K, bias)."""
+       decode_qkv (32 tokens, bias, no-split kernel), decode_o (32 tokens, residual, no-split kernel)."""
 import sys
 from pathlib import Path
 
@@ -25,6 +25,9 @@ elif case in ("prefill_down", "decode_down"):
 elif case == "decode_qkv":
     x, w, b = g(32, 3584, sc=1.0), g(4608, 3584), g(4608, sc=0.3)
     fn = lambda: ops.linear(x, w, b)  # noqa: E731
+elif case == "decode_o":
+    x, w, r = g(32, 3584, sc=1.0), g(3584, 3584), g(32, 3584, sc=1.0)
+    fn = lambda: ops.linear(x, w, resid=r, out=r)  # noqa: E731
 else:
     raise SystemExit(f"unknown case {case}")
 for _ in range(3):
