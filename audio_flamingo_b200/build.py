@@ -20,7 +20,6 @@ LIB = PKG_DIR / "libaf3b200.so"
 SOURCES = [
     "common.cu",
     "gemm_tcgen05.cu",
-    "gemm_skinny_tcgen05.cu",
     "attention_tcgen05.cu",
     "attention_v2_tcgen05.cu",
     "decode_attention.cu",

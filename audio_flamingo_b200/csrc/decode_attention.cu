@@ -10,7 +10,7 @@
 //     S^T[key, head] = K_tile[key, :] . Q[head, :]          tcgen05.mma 128x16x16 x 8,  A = K tile (K-major, via TMA)
 //     O^T[dim, head] = V_tile^T[dim, key] . P^T[key, head]   tcgen05.mma 128x16x16 x 8,  A = V tile read MN-major
 // so K and V never pass through registers.  Roles: warps 0-3 softmax + accumulation (thread = key lane for S, = output
-// dim lane for O), warp 4 issues the MMAs, warp 5 the TMA loads.  S, P and the per-chunk O are double-buffered so that
+// dim lane for O; the heads are split between two warp groups, see below), warp 8 issues the MMAs, warp 9 the TMA loads.  S, P and the per-chunk O are double-buffered so that
 // S_{i+1} = K_{i+1} Q^T and the loads run ahead of softmax_i, and O_i is folded into the register accumulator after
 // softmax_{i+1} has been handed to the tensor core (the chunk's P.V product is then long complete).
 // Splits: the host picks nz = min(chunks(Tmax), SMs / (B*Hkv)) so that B*Hkv*nz CTAs (one per SM, 207 KB of smem) cover
@@ -31,7 +31,7 @@ namespace af3 {
 constexpr int DA_CHUNK = 128;    // keys per ring stage
 constexpr int DA_NH = 16;        // query heads per KV head, padded (UMMA N)
 constexpr int DA_NS_MAX = 3;     // K/V ring stages (template parameter NS: 2 or 3)
-constexpr int DA_THREADS = 192;  // warps 0-3: softmax / accumulate (thread = TMEM lane), warp 4: MMA issue, warp 5: TMA
+constexpr int DA_THREADS = 320;  // warps 0-7: softmax / accumulate (thread = TMEM lane x head group), warp 8: MMA issue, warp 9: TMA
 constexpr int DA_D = 128;
 constexpr int DA_STAGE = 2 * DA_CHUNK * DA_D * 2;  // K tile + V tile
 constexpr int da_smem(int ns) {
@@ -46,6 +46,23 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
           "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr)
         : "memory");
+}
+
+// 32 lanes x N consecutive columns (N = 4 or 8)
+template <int N>
+__device__ __forceinline__ void tmem_ldn(uint32_t taddr, uint32_t (&v)[N]) {
+    static_assert(N == 4 || N == 8, "tmem_ldn");
+    if constexpr (N == 4) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+                     : "r"(taddr)
+                     : "memory");
+    } else {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                     : "r"(taddr)
+                     : "memory");
+    }
 }
 
 // Merge of the split partials of one (sequence, KV head), executed by the last-arriving split CTA.  Partial layout
@@ -104,19 +121,23 @@ __device__ __forceinline__ float da_exp2(float x) {
     return y;
 }
 
-// NG = query heads handled per thread (8 when G <= 8, else 16).  The per-head loops are branch-free over NG so the NG
-// independent shuffle / SFU chains interleave: with one CTA per SM each softmax warp is alone on its scheduler and every
-// dependent-instruction latency is otherwise exposed (ncu r01b: 90 % of the softmax warps' samples sat in those chains).
+// NG = padded query heads per KV head (8 when G <= 8, else 16).  The per-head loops are branch-free so the independent shuffle /
+// SFU chains interleave (ncu r01b: 90 % of the softmax warps' samples sat in those chains).
+// Two warp groups split the heads (round 2): the in-graph timeline showed the kernel bound by the softmax warps' serial work per
+// 128-key chunk (~2 us x 7 chunks at context 800, the K/V ring far ahead), not by the stream.  Warps 0-3 take heads [0, NG/2), warps
+// 4-7 heads [NG/2, NG) of the same keys / output dims (warp w and w + 4 share a TMEM lane quarter): half the instructions per
+// thread and chunk, two warps per scheduler, and the two groups only meet at the P hand-off (each has its own named barrier).
 template <int NG, int DA_NS>
 __global__ void __launch_bounds__(DA_THREADS, 1)
 decode_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                    const __grid_constant__ CUtensorMap map_v, float* __restrict__ part, bf16* __restrict__ out,
                    int* __restrict__ counters, int H, int Hkv, int nz, const int* __restrict__ ctx_len_p,
-                   const int* __restrict__ kv_start, float scale_log2, unsigned long long* trace) {
+                   const int* __restrict__ kv_start, float scale_log2, unsigned long long* trace, int l2_prefetch) {
     constexpr int D = DA_D;
     const int G = H / Hkv;
     const int b = blockIdx.x, hk = blockIdx.y, sp = blockIdx.z;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NH = NG / 2;  // heads per softmax thread
     if (tid == 0) trace_mark(trace, 0);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -131,7 +152,7 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     __shared__ int last_flag;
 
     // ---- prologue (no global-memory reads: overlaps the tail of the previous kernel under PDL)
-    if (tid == 128) {
+    if (tid == 256) {
         tma_prefetch_desc(&map_q);
         tma_prefetch_desc(&map_k);
         tma_prefetch_desc(&map_v);
@@ -143,7 +164,7 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(s_full + s, 1);
-            mbar_init(p_full + s, 128);
+            mbar_init(p_full + s, 256);
             mbar_init(o_full + s, 1);
         }
         fence_barrier_init();
@@ -157,6 +178,24 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     tc_fence_after();
     const uint32_t tmem_S = *tmem_slot, tmem_O = tmem_S + 2 * DA_NH;  // S0 S1 O0 O1, 16 columns each
     pdl_launch_dependents();
+    if (l2_prefetch && warp == 9 && lane == 0) {
+        // Before the dependency resolves: ask L2 for this CTA's K/V chunks.  Only a hint -- nothing is read into the SM, so it does not
+        // matter that ctx_len may still hold the previous step's value or that the row the q/k/v projection is appending right now is
+        // not there yet (its write lands in the same L2 line; the real loads below come after griddepcontrol.wait).
+        const int ctx0 = *reinterpret_cast<const volatile int*>(ctx_len_p);
+        const int start0 = kv_start ? kv_start[b] : 0;
+        const int lo0 = start0 / DA_CHUNK, hi0 = (ctx0 + DA_CHUNK - 1) / DA_CHUNK;
+        const int live0 = max(hi0 - lo0, 0), cps0 = (live0 + nz - 1) / nz;
+        const int beg0 = lo0 + sp * cps0, n0 = max(min(hi0, beg0 + cps0) - beg0, 0);
+        for (int i = 0; i < n0; ++i) {
+            const int row = (beg0 + i) * DA_CHUNK;
+#pragma unroll
+            for (int db = 0; db < 2; ++db) {
+                tma_prefetch_l2_3d(&map_k, db * 64, row, b * Hkv + hk);
+                tma_prefetch_l2_3d(&map_v, db * 64, row, b * Hkv + hk);
+            }
+        }
+    }
     pdl_wait();
     if (tid == 0) trace_mark(trace, 1);
 
@@ -171,7 +210,7 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     const int n = max(min(c_hi, c_beg + cps) - c_beg, 0);
 
     if (n > 0) {
-        if (warp == 5) {
+        if (warp == 9) {
             if (lane == 0) {
                 mbar_arrive_expect_tx(q_full, 2 * DA_NH * 128);
 #pragma unroll
@@ -190,7 +229,7 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 }
             }
             __syncwarp();
-        } else if (warp == 4) {
+        } else if (warp == 8) {
             if (lane == 0) {
                 constexpr uint32_t idesc_s = make_idesc_bf16(128, DA_NH, 0, 0);
                 constexpr uint32_t idesc_o = make_idesc_bf16(128, DA_NH, 1, 0);  // A (= V tile) is MN-major
@@ -228,72 +267,77 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             }
             __syncwarp();
         } else {
-            // ---- online softmax: thread = key (TMEM lane) for S, = output dim for O; columns = heads
-            const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
-            float m_run[NG], m_prev[NG], m_pp[NG], l_thr[NG], acc[NG];
+            // ---- online softmax: thread = key (TMEM lane) for S, = output dim for O; columns = heads [hg * NH, hg * NH + NH)
+            const int wq = warp & 3, hg = warp >> 2;
+            const int kt = wq * 32 + lane;  // key within the chunk / output dim
+            const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
+            const uint32_t col_off = hg * NH;
+            const int bar_id = 1 + hg;      // named barrier of this head group's four warps
+            float m_run[NH], m_prev[NH], m_pp[NH], l_thr[NH], acc[NH];
 #pragma unroll
-            for (int g = 0; g < NG; ++g) {
+            for (int g = 0; g < NH; ++g) {
                 m_run[g] = -INFINITY;   // running max after the current chunk
                 m_prev[g] = -INFINITY;  // ... one chunk back (what O_{i-1} is relative to)
                 m_pp[g] = -INFINITY;    // ... two chunks back (what acc is relative to when O_{i-1} is folded in)
                 l_thr[g] = 0.f;         // this key lane's share of the softmax denominator
                 acc[g] = 0.f;           // this output dim's running numerator
             }
-            {   // P rows of heads >= NG are never written again: zero them once in both buffers
-                const int kc = tid & 63;
+            if (hg == 0) {   // P rows of heads >= NG are never written again: zero them once in both buffers
+                const int kc = kt & 63;
 #pragma unroll
                 for (int pb = 0; pb < 2; ++pb) {
-                    uint8_t* blk = sP + pb * (2 * DA_NH * 128) + (tid >> 6) * (DA_NH * 128);
+                    uint8_t* blk = sP + pb * (2 * DA_NH * 128) + (kt >> 6) * (DA_NH * 128);
 #pragma unroll
                     for (int g = NG; g < DA_NH; ++g)
                         *reinterpret_cast<bf16*>(blk + g * 128 + ((((kc >> 3) ^ (g & 7)) << 4) | ((kc & 7) << 1))) = __float2bfloat16_rn(0.f);
                 }
             }
             // acc is relative to m_from (the running max at its last update); O_j is relative to m_to
-            auto accumulate = [&](int j, const float (&m_from)[NG], const float (&m_to)[NG]) {
+            auto accumulate = [&](int j, const float (&m_from)[NH], const float (&m_to)[NH]) {
                 mbar_wait(o_full + (j & 1), (j >> 1) & 1);
                 tc_fence_after();
-                uint32_t ov[16];
-                tmem_ld16(tmem_O + (j & 1) * DA_NH + lane_off, ov);
+                uint32_t ov[NH];
+                tmem_ldn<NH>(tmem_O + (j & 1) * DA_NH + col_off + lane_off, ov);
                 tmem_ld_wait();
 #pragma unroll
-                for (int g = 0; g < NG; ++g) {
+                for (int g = 0; g < NH; ++g) {
                     const float a = (m_from[g] == -INFINITY) ? 0.f : da_exp2(m_from[g] - m_to[g]);
                     acc[g] = fmaf(acc[g], a, __uint_as_float(ov[g]));
                 }
             };
             for (int i = 0; i < n; ++i) {
-                const int j = (c_beg + i) * DA_CHUNK + tid;
+                const int j = (c_beg + i) * DA_CHUNK + kt;
                 const bool valid = j >= start && j < ctx;
                 float* redm = red + (i & 1) * 64;
                 mbar_wait(s_full + (i & 1), (i >> 1) & 1);
                 tc_fence_after();
-                uint32_t sv[16];
-                tmem_ld16(tmem_S + (i & 1) * DA_NH + lane_off, sv);
+                uint32_t sv[NH];
+                tmem_ldn<NH>(tmem_S + (i & 1) * DA_NH + col_off + lane_off, sv);
                 tmem_ld_wait();
-                float t[NG], mx[NG];
+                float t[NH], mx[NH];
 #pragma unroll
-                for (int g = 0; g < NG; ++g) {
-                    t[g] = (valid && g < G) ? __uint_as_float(sv[g]) * scale_log2 : -INFINITY;
+                for (int g = 0; g < NH; ++g) {
+                    t[g] = (valid && hg * NH + g < G) ? __uint_as_float(sv[g]) * scale_log2 : -INFINITY;
                     mx[g] = t[g];
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-                    for (int g = 0; g < NG; ++g) mx[g] = fmaxf(mx[g], __shfl_xor_sync(0xffffffffu, mx[g], o));
+                    for (int g = 0; g < NH; ++g) mx[g] = fmaxf(mx[g], __shfl_xor_sync(0xffffffffu, mx[g], o));
                 }
-                if (lane < NG) {  // lane g publishes head g's warp maximum (all lanes hold it after the butterfly)
+                if (lane < NH) {  // lane g publishes head g's warp maximum (all lanes hold it after the butterfly)
                     float v = mx[0];
 #pragma unroll
-                    for (int g = 1; g < NG; ++g) v = (lane == g) ? mx[g] : v;
-                    redm[warp * DA_NH + lane] = v;
+                    for (int g = 1; g < NH; ++g) v = (lane == g) ? mx[g] : v;
+                    redm[wq * DA_NH + col_off + lane] = v;
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                uint8_t* blk = sP + (i & 1) * (2 * DA_NH * 128) + (tid >> 6) * (DA_NH * 128);
-                const int kc = tid & 63;
+                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                uint8_t* blk = sP + (i & 1) * (2 * DA_NH * 128) + (kt >> 6) * (DA_NH * 128);
+                const int kc = kt & 63;
 #pragma unroll
-                for (int g = 0; g < NG; ++g) {
-                    const float mc = fmaxf(fmaxf(redm[g], redm[DA_NH + g]), fmaxf(redm[2 * DA_NH + g], redm[3 * DA_NH + g]));
+                for (int g = 0; g < NH; ++g) {
+                    const int gh = col_off + g;  // head within the KV group
+                    const float mc = fmaxf(fmaxf(redm[gh], redm[DA_NH + gh]), fmaxf(redm[2 * DA_NH + gh], redm[3 * DA_NH + gh]));
                     const float m_new = fmaxf(m_run[g], mc);
                     const float a = (m_run[g] == -INFINITY) ? 0.f : da_exp2(m_run[g] - m_new);
                     const float p = (t[g] == -INFINITY) ? 0.f : da_exp2(t[g] - m_new);  // masked keys / padded heads -> 0
@@ -301,8 +345,8 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                     m_pp[g] = m_prev[g];
                     m_prev[g] = m_run[g];
                     m_run[g] = m_new;
-                    // P^T[key = tid][head g] -> B tile [16 heads][128 keys], K-major, 128B swizzle: row g, key column tid
-                    *reinterpret_cast<bf16*>(blk + g * 128 + ((((kc >> 3) ^ (g & 7)) << 4) | ((kc & 7) << 1))) = __float2bfloat16_rn(p);
+                    // P^T[key = kt][head gh] -> B tile [16 heads][128 keys], K-major, 128B swizzle: row gh, key column kt
+                    *reinterpret_cast<bf16*>(blk + gh * 128 + ((((kc >> 3) ^ (gh & 7)) << 4) | ((kc & 7) << 1))) = __float2bfloat16_rn(p);
                 }
                 fence_proxy_async_smem();
                 tc_fence_before();
@@ -317,25 +361,26 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-                for (int g = 0; g < NG; ++g) l_thr[g] += __shfl_xor_sync(0xffffffffu, l_thr[g], o);
+                for (int g = 0; g < NH; ++g) l_thr[g] += __shfl_xor_sync(0xffffffffu, l_thr[g], o);
             }
-            if (lane < NG) {
+            if (lane < NH) {
                 float v = l_thr[0];
 #pragma unroll
-                for (int g = 1; g < NG; ++g) v = (lane == g) ? l_thr[g] : v;
-                reds[warp * DA_NH + lane] = v;
+                for (int g = 1; g < NH; ++g) v = (lane == g) ? l_thr[g] : v;
+                reds[wq * DA_NH + col_off + lane] = v;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
 #pragma unroll
-            for (int g = 0; g < NG; ++g) {
-                if (g < G) {
-                    const float L = reds[g] + reds[DA_NH + g] + reds[2 * DA_NH + g] + reds[3 * DA_NH + g];
+            for (int g = 0; g < NH; ++g) {
+                const int gh = col_off + g;
+                if (gh < G) {
+                    const float L = reds[gh] + reds[DA_NH + gh] + reds[2 * DA_NH + gh] + reds[3 * DA_NH + gh];
                     if (nz == 1) {
-                        out[(static_cast<size_t>(b) * H + hk * G + g) * D + tid] = __float2bfloat16_rn(L > 0.f ? acc[g] / L : 0.f);
+                        out[(static_cast<size_t>(b) * H + hk * G + gh) * D + kt] = __float2bfloat16_rn(L > 0.f ? acc[g] / L : 0.f);
                     } else {
-                        float* dst = part + ((static_cast<size_t>(b) * H + hk * G + g) * nz + sp) * (D + 4);
-                        dst[tid] = acc[g];
-                        if (tid == 0) {
+                        float* dst = part + ((static_cast<size_t>(b) * H + hk * G + gh) * nz + sp) * (D + 4);
+                        dst[kt] = acc[g];
+                        if (kt == 0) {
                             dst[D] = m_run[g];
                             dst[D + 1] = L;
                         }
@@ -411,7 +456,8 @@ int decode_attention(cudaStream_t stream, const bf16* qkv, const bf16* k_cache, 
     int* counters = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(scratch) + partial_bytes(B, H, D, Tmax));
     auto kern = (H / Hkv <= 8) ? decode_attn_kernel<8, 3> : decode_attn_kernel<16, 3>;
     AF3_CHECK_CUDA(launch_kernel(kern, grid, dim3(DA_THREADS), da_smem(ns), stream, mq, mk, mv, scratch, out, counters, H, Hkv, nz,
-                                 ctx_len, kv_start, scale * 1.4426950408889634f, trace_next_slot()));
+                                 ctx_len, kv_start, scale * 1.4426950408889634f, trace_next_slot(),
+                                 [] { const char* e = getenv("AF3_L2_PREFETCH_KV"); return e ? atoi(e) : 0; }()));
     return 0;
 }
 

@@ -1,4 +1,4 @@
-// Epilogue flags and side-argument structs shared by the GEMM translation units (gemm_tcgen05.cu, gemm_skinny_tcgen05.cu) and
+// Epilogue flags and side-argument structs shared by the GEMM translation units (gemm_tcgen05.cu) and
 // the C ABI (af3_abi.cu); the flag values are the AF3_EPI_* constants of include/af3b200.h.
 #pragma once
 #include "common.h"
@@ -31,11 +31,5 @@ int gemm_bf16(cudaStream_t stream, const bf16* x, int ldx, const bf16* w, int ld
               int n_feat, int K, int flags, const bf16* bias, const bf16* resid, int ld_res, int res_period,
               void* workspace, size_t workspace_bytes, const RopeEpilogue* rope, const NormFusion* nf);
 size_t gemm_workspace_bytes();
-
-// no-split-K few-token path (gemm_skinny_tcgen05.cu)
-bool gemm_skinny_applies(int n_tok, int n_feat, int K, int flags, int ldx, int ldw, int ldo, int ld_res, int res_period, const void* x,
-                         const void* w, const void* out, const void* bias, const void* resid);
-int gemm_skinny(cudaStream_t stream, const bf16* x, int ldx, const bf16* w, int ldw, bf16* out, int ldo, int n_tok, int n_feat, int K,
-                int flags, const bf16* bias, const bf16* resid, int ld_res, const RopeEpilogue* rope);
 
 }  // namespace af3

@@ -52,6 +52,10 @@ struct GemmArgs {
     // by two TMA boxes, and gate_proj.weight / up_proj.weight can simply be VIEWS of the fused matrix (no second copy in HBM)
     int swiglu_up_row0;
     int k_splits;
+    // few-token mode: weight k-blocks BEYOND the shared-memory ring that the producer also requests into L2 before
+    // griddepcontrol.wait (cp.async.bulk.prefetch.tensor): under programmatic dependent launch the CTA is resident long before its
+    // dependency resolves (9-15 us for q/k/v, o and gate/up: profiles/*decode_timeline*) with HBM idle during the predecessor's tail
+    int l2_prefetch;
     // cluster_reduce (EXPERIMENT, off by default -- measured slower, see gemm_bf16()): the k_splits CTAs of a tile form a thread-block
     // cluster and exchange their fp32 partial tiles through distributed shared memory: CTA q of the cluster receives everyone's
     // partials for ITS slice of the 32 tokens, sums them in split order (deterministic) and runs the fused epilogue for that slice.
@@ -220,6 +224,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
                         for (int na = 0; na < NA; ++na)
                             tma_load_2d(sR + na * 128 * BK * 2, &map_r, &full[prefetched], kb * BK,
                                         a.swiglu_up_row0 ? na * a.swiglu_up_row0 + r * 128 : (r * NA + na) * 128);
+                    }
+                    int pf = a.l2_prefetch;
+                    for (int kb = kb_lo(sp) + prefetched; kb < kb_lo(sp + 1) && pf > 0; ++kb, --pf) {
+#pragma unroll
+                        for (int na = 0; na < NA; ++na)
+                            tma_prefetch_l2_2d(&map_r, kb * BK, a.swiglu_up_row0 ? na * a.swiglu_up_row0 + r * 128 : (r * NA + na) * 128);
                     }
                 }
             }
@@ -1035,13 +1045,6 @@ int gemm_bf16(cudaStream_t stream, const bf16* x, int ldx, const bf16* w, int ld
     AF3_REQUIRE(!(flags & EPI_SWIGLU_CONCAT) || (swiglu && n_feat % 128 == 0), "gemm: the [gate; up] layout needs SwiGLU and n_feat % 128 == 0");
     flags &= ~EPI_SWIGLU_CONCAT;
     const int w_rows = swiglu ? 2 * ceil_div(n_feat, 128) * 128 : n_feat;
-    // short-K few-token projections (q/k/v, o of the decode step): one CTA per 32 weight rows over the full K, no split-K tail
-    if (n_tok <= 64 && !swiglu && !nf && gemm_skinny_applies(n_tok, n_feat, K, flags, ldx, ldw, ldo, ld_res, res_period, x, w, out, bias, resid)) {
-        if (flags & EPI_ROPE)
-            AF3_REQUIRE(rope && rope->cs && rope->k_cache && rope->v_cache && rope->pos && n_feat == (rope->H + 2 * rope->Hkv) * 128,
-                        "gemm: EPI_ROPE is the few-token fused q/k/v projection with head_dim 128");
-        return gemm_skinny(stream, x, ldx, w, ldw, reinterpret_cast<bf16*>(out), ldo, n_tok, n_feat, K, flags, bias, resid, ld_res, rope);
-    }
     GemmArgs a{};
     a.K = K;
     a.n_tok = n_tok;
@@ -1122,6 +1125,7 @@ int gemm_bf16(cudaStream_t stream, const bf16* x, int ldx, const bf16* w, int ld
     constexpr int BN = 32;
     a.R = w_rows;
     a.C = n_tok;
+    a.l2_prefetch = [&] { const char* e = getenv(swiglu ? "AF3_L2_PREFETCH_GU" : "AF3_L2_PREFETCH"); return e ? atoi(e) : 0; }();
     a.num_c_tiles = ceil_div(n_tok, BN);
     a.group_r = 1;
     if (int e = make_tmap_2d(&mw, w, K, w_rows, ldw, BK, 128)) return e;

@@ -747,7 +747,7 @@ class AudioFlamingo3ForConditionalGeneration(nn.Module):
             # the captured graph holds raw addresses: key it on the weight storages too, so a re-pack (load_reference_state_dict) or
             # a move (.to()) can never leave a stale graph replaying against freed memory
             key = (B, Tmax, use_graph, os.environ.get("AF3_PDL", "1") != "0", os.environ.get("AF3_FUSE_NORM", "0") == "1",
-                   os.environ.get("AF3_SKINNY_MAXK", ""), str(dev), lm.lm_head.weight.data_ptr(), lm._packed[0][0].data_ptr(), lm._packed[-1][2].data_ptr())
+                   "|".join(os.environ.get(k, "") for k in ("AF3_L2_PREFETCH", "AF3_L2_PREFETCH_GU", "AF3_L2_PREFETCH_KV")), str(dev), lm.lm_head.weight.data_ptr(), lm._packed[0][0].data_ptr(), lm._packed[-1][2].data_ptr())
             st = self._decode_state
             if st is not None and st["key"] == key:
                 cache, step_fn = st["cache"], st["step"]       # same buffers -> the captured graph is valid as it stands

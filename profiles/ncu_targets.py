@@ -1,7 +1,7 @@
 """Single-kernel targets for `ncu --set full` at the bench's shapes (one warm-up launch, then two launches of the case):
     ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 1 -c 1 -o gpurun_out/X python profiles/ncu_targets.py prefill_gateup
 cases: prefill_gateup (24960 x 2*18944 x 3584, SwiGLU, token-major), prefill_down, decode_gateup (32 tokens), decode_down (split-K),
-       decode_qkv (32 tokens, bias, no-split kernel), decode_o (32 tokens, residual, no-split kernel)."""
+       decode_qkv (split-K, bias), decode_o (split-K, residual)."""
 import sys
 from pathlib import Path
 
