@@ -457,7 +457,7 @@ int decode_attention(cudaStream_t stream, const bf16* qkv, const bf16* k_cache, 
     auto kern = (H / Hkv <= 8) ? decode_attn_kernel<8, 3> : decode_attn_kernel<16, 3>;
     AF3_CHECK_CUDA(launch_kernel(kern, grid, dim3(DA_THREADS), da_smem(ns), stream, mq, mk, mv, scratch, out, counters, H, Hkv, nz,
                                  ctx_len, kv_start, scale * 1.4426950408889634f, trace_next_slot(),
-                                 [] { const char* e = getenv("AF3_L2_PREFETCH_KV"); return e ? atoi(e) : 0; }()));
+                                 [] { const char* e = getenv("AF3_L2_PREFETCH_KV"); return e ? atoi(e) : 1; }()));   // on: -21 us per step in two A/B pairs (profiles/r02n_*)
     return 0;
 }
 

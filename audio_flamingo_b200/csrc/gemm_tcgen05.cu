@@ -80,7 +80,7 @@ struct GemmArgs {
 
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle atom row
 
-template <int BN, int NA, int STAGES, bool SWAP>
+template <int BN, int NA, int STAGES, bool SWAP, bool EXP = false>
 struct GemmCfg {
     static constexpr int R_BYTES = 128 * NA * BK * 2;
     static constexpr int C_BYTES = BN * BK * 2;
@@ -91,12 +91,14 @@ struct GemmCfg {
     // swap mode: one [32 tokens x 128 features] bf16 tile to transpose the accumulator for token-major vector I/O
     // + (few-token, NA = 1) the landing zone of the cluster split-K reduction: [k_splits][ceil(32 / k_splits)][128] fp32 partial
     //   slices written by the peer CTAs through distributed shared memory (<= 18.5 KB for 2..8 splits)
-    static constexpr int ZONE_BYTES = (SWAP && NA == 1) ? 19456 : 0;
+    //   -- experiment instantiations only; the default few-token kernel spends that shared memory on two more ring stages
+    static constexpr int ZONE_BYTES = (SWAP && NA == 1 && EXP) ? 19456 : 0;
     static constexpr int EPI_STAGE_BYTES = (SWAP ? 32 * 128 * 2 : 4 * 2 * 4096) + ZONE_BYTES;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers: (4 STAGES + 12) x 8 B + slot*/;
     static_assert((4 * STAGES + 12) * 8 + 16 <= 512, "barrier area");
     static_assert(2 * ACC_COLS <= 512, "TMEM budget");
     static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
+    static_assert(SMEM_BYTES <= 232448, "shared memory per CTA");
 };
 
 __device__ __forceinline__ void tile_coords(int t, const GemmArgs& a, int& r, int& c) {
@@ -137,7 +139,7 @@ template <int BN, int NA, int STAGES, bool SWAP, int EPI, int EW, bool EXP = fal
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_c,
             const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res, const GemmArgs a) {
-    using Cfg = GemmCfg<BN, NA, STAGES, SWAP>;
+    using Cfg = GemmCfg<BN, NA, STAGES, SWAP, EXP>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* epi_stage = smem + STAGES * Cfg::STAGE_BYTES;
@@ -931,7 +933,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ C
 template <int BN, int NA, int STAGES, bool SWAP, int EPI, int EW = 4, bool EXP = false>
 static int launch_epi(const CUtensorMap& mr, const CUtensorMap& mc, const CUtensorMap& mo, const CUtensorMap& mres,
                   const GemmArgs& a, cudaStream_t stream) {
-    using Cfg = GemmCfg<BN, NA, STAGES, SWAP>;
+    using Cfg = GemmCfg<BN, NA, STAGES, SWAP, EXP>;
     auto kern = gemm_kernel<BN, NA, STAGES, SWAP, EPI, EW, EXP>;
     static DeviceOnce once;
     if (once.first()) {
@@ -981,17 +983,13 @@ static int launch_epi(const CUtensorMap& mr, const CUtensorMap& mc, const CUtens
 // Host entry.  x: [n_tok, K] bf16 (pitch ldx), w: [n_rows_w, K] bf16 (pitch ldw) where n_rows_w = n_feat, or the
 // gate/up-interleaved 2*ceil(n_feat/128)*128 rows when EPI_SWIGLU.  out: [n_tok, n_feat] (pitch ldo).
 // compile-time epilogue specialisations for the flag sets the AF3 path uses; anything else -> generic (-1)
-template <int BN, int NA, int STAGES, bool SWAP>
+template <int BN, int NA, int STAGES, bool SWAP, bool EXP = false>
 static int launch(const CUtensorMap& mr, const CUtensorMap& mc, const CUtensorMap& mo, const CUtensorMap& mres,
                   const GemmArgs& a, cudaStream_t stream) {
-    // few-token kernels: the experiments (RMSNorm fusion, cluster split-K) live in their own instantiations
-    [[maybe_unused]] const bool exp = SWAP && (a.norm_w || a.sumsq_out || a.cluster_reduce);
-#define AF3_EPI_CASE(F)                                                                                      \
-    case (F):                                                                                                \
-        if constexpr (SWAP) {                                                                                \
-            if (exp) return launch_epi<BN, NA, STAGES, SWAP, (F), 4, true>(mr, mc, mo, mres, a, stream);     \
-        }                                                                                                    \
-        return launch_epi<BN, NA, STAGES, SWAP, (F)>(mr, mc, mo, mres, a, stream);
+    // few-token kernels: the experiments (RMSNorm fusion, cluster split-K) live in their own instantiations (EXP)
+#define AF3_EPI_CASE(F) \
+    case (F):           \
+        return launch_epi<BN, NA, STAGES, SWAP, (F), 4, EXP>(mr, mc, mo, mres, a, stream);
     if constexpr (!SWAP) {
         // 8 epilogue warps where the epilogue (not the MMA) bounds the tile: TMA-store path without a TMA residual
         if (a.tma_epi && !((a.flags & EPI_RESID) && a.res_period == 0)) {
@@ -1025,10 +1023,7 @@ static int launch(const CUtensorMap& mr, const CUtensorMap& mc, const CUtensorMa
         }
     }
 #undef AF3_EPI_CASE
-    if constexpr (SWAP) {
-        if (exp) return launch_epi<BN, NA, STAGES, SWAP, -1, 4, true>(mr, mc, mo, mres, a, stream);
-    }
-    return launch_epi<BN, NA, STAGES, SWAP, -1>(mr, mc, mo, mres, a, stream);
+    return launch_epi<BN, NA, STAGES, SWAP, -1, 4, EXP>(mr, mc, mo, mres, a, stream);
 }
 
 size_t gemm_workspace_bytes() { return (8u << 20) + 4096 * sizeof(int); }
@@ -1130,14 +1125,14 @@ int gemm_bf16(cudaStream_t stream, const bf16* x, int ldx, const bf16* w, int ld
     a.group_r = 1;
     if (int e = make_tmap_2d(&mw, w, K, w_rows, ldw, BK, 128)) return e;
     if (int e = make_tmap_2d(&mx, x, K, n_tok, ldx, BK, BN)) return e;
-    // Pipeline depth of the few-token mode: 8 x 20 KB (NA = 1) / 6 x 36 KB (NA = 2) stages.  Shallower rings (4 / 3 stages, so that
+    // Pipeline depth of the few-token mode: 10 x 20 KB (NA = 1) / 6 x 36 KB (NA = 2) stages.  Shallower rings (4 / 3 stages, so that
     // the NEXT kernel of the decode chain could be co-resident and prefetch under programmatic dependent launch) were measured
     // in round 2 and are slower: a single SM pulls at most ~58 GB/s from HBM (profiles/r02b_microbench_splitk.json), the streams
     // need the deep ring, and the co-resident successor does not shorten the dependent tails (profiles/r02a_decode_timeline_*.md).
     if (swiglu) {
         a.num_r_tiles = ceil_div(w_rows, 256);
         AF3_REQUIRE(!a.norm_w || a.num_r_tiles * a.num_c_tiles <= sm_count(), "gemm: fused RMSNorm needs one work item per CTA");
-        return launch<BN, 2, 6, true>(mw, mx, mw, mw, a, stream);
+        return (a.norm_w || a.sumsq_out) ? launch<BN, 2, 6, true, true>(mw, mx, mw, mw, a, stream) : launch<BN, 2, 6, true>(mw, mx, mw, mw, a, stream);
     }
     a.num_r_tiles = ceil_div(w_rows, 128);
     // split-K when the tile grid cannot fill the GPU and a (zero-initialised) workspace was supplied
@@ -1166,7 +1161,10 @@ int gemm_bf16(cudaStream_t stream, const bf16* x, int ldx, const bf16* w, int ld
         }
     }
     AF3_REQUIRE(!a.norm_w || a.num_r_tiles * a.num_c_tiles * a.k_splits <= sm_count(), "gemm: fused RMSNorm needs one work item per CTA");
-    return launch<BN, 1, 8, true>(mw, mx, mw, mw, a, stream);
+    // ring depth: 10 x 20 KB = 200 KB in flight per SM (the few-token streams are latency-bound on bytes in flight); the experiment
+    // instantiations keep 8 stages next to their 19 KB exchange zone
+    if (a.norm_w || a.sumsq_out || a.cluster_reduce) return launch<BN, 1, 8, true, true>(mw, mx, mw, mw, a, stream);
+    return launch<BN, 1, 10, true>(mw, mx, mw, mw, a, stream);
 }
 
 }  // namespace af3

@@ -70,6 +70,14 @@ class DecodeTrace:
                        "wait_min": int(pos(1).min()) if len(pos(1)) else None, "wait_max": int(pos(1).max()) if len(pos(1)) else None,
                        "mid_max": int(pos(2).max()) if len(pos(2)) else None,
                        "exit_min": int(pos(3).min()) if len(pos(3)) else None, "exit_max": int(pos(3).max()) if len(pos(3)) else None}
+                both = live & (m[:, 2] > 0) & (m[:, 3] > 0)
+                if both.any():
+                    # per-CTA time from "own accumulator ready" to "own exit" (us): the split-K kernels' non-reducing CTAs show the
+                    # cost of publishing a partial (store, fence, counter), the reducing ones the whole tail
+                    d = np.sort((m[both, 3] - m[both, 2]) / 1e3)
+                    rec["cta_tail_us"] = {"min": float(d[0]), "p25": float(d[len(d) // 4]), "median": float(d[len(d) // 2]),
+                                          "p75": float(d[(3 * len(d)) // 4]), "max": float(d[-1])}
+                    rec["mid_spread_us"] = float((m[both, 2].max() - m[both, 2].min()) / 1e3)
                 out.append(rec)
         if not out:
             return out
