@@ -80,6 +80,9 @@ def main():
         top = ", ".join(f"{k[6:]} {v}" for k, v in sorted(st.items(), key=lambda kv: -kv[1])[:2] if v)
         lines.append(f"| {100 * s / tot:.1f} % | {n} | `{s_[:70]}` | {top} |")
     open(dst, "w").write("\n".join(lines) + "\n")
+    import json
+    json.dump({"kernel": kname[:200], "report": rep, "note": note, "metrics": {k: {"value": metric[k][0], "unit": metric[k][1]} for k in want if k in metric},
+               "warp_instructions": n_inst, "sample_groups": {k: v / tot for k, v in grp.items()}}, open(dst.rsplit(".", 1)[0] + ".json", "w"), indent=1)
     print("\n".join(lines[:30]))
 
 
