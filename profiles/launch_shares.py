@@ -6,7 +6,7 @@ import csv
 import re
 import sys
 
-DECODE = re.compile(r"gemm_kernel<\(int\)32,|decode_attn_kernel|rmsnorm_rowblock_kernel|rope_table_kernel|argmax_(partial|final)_kernel")
+DECODE = re.compile(r"gemm_kernel<(\(int\))?32,|decode_attn_kernel|rmsnorm_rowblock_kernel|rope_table_kernel|argmax_(partial|final)_kernel")
 NEW_TOKENS = 128
 
 
