@@ -45,6 +45,7 @@ SIGNATURES = {
     "af3_embed_scatter": (_i, [_p, _p, _i, _p, _i, _i64, _p, _i, _i, _p, _p, _p, _p]),
     "af3_argmax_scratch_bytes": (_sz, [_i]),
     "af3_argmax": (_i, [_p, _p, _i, _i, _p, _p]),
+    "af3_token_step": (_i, [_p, _p, _i, _p, _p, _p, _p, _i, _p, _p, _p]),
 }
 
 class GemmFusion(C.Structure):

@@ -10,6 +10,8 @@ int rotary_time(cudaStream_t stream, bf16* x, const float* ts, const float* inv_
                 float window_duration, float max_len);
 int gated_residual(cudaStream_t stream, const bf16* resid, const bf16* y, const bf16* alpha, int alpha_scalar, const int* row_gate,
                    bf16* out, int rows, int dim);
+int token_step(cudaStream_t stream, const int64_t* raw_ids, int B, int* unfinished, const int64_t* eos, const int64_t* ctl,
+               int64_t* tok_buf, int cap, int* gen_idx, int64_t* ids_out, int* done_flags);
 int rope_table(cudaStream_t stream, float* cs, int B, int D, const int* pos_dev, const int* kv_start, const float* inv_freq);
 int trace_begin(void* buf, size_t bytes);
 int trace_end();
@@ -45,7 +47,7 @@ using af3::bf16;
 extern "C" {
 
 const char* af3_last_error(void) { return af3::last_error_cstr(); }
-int af3_abi_version(void) { return 2; }
+int af3_abi_version(void) { return 3; }
 void af3_set_pdl(int enable) { af3::set_pdl(enable != 0); }
 size_t af3_trace_slot_bytes(void) { return sizeof(unsigned long long) * af3::TRACE_CTAS * af3::TRACE_MARKS; }
 int af3_trace_begin(void* buf, size_t bytes) { return af3::trace_begin(buf, bytes); }
@@ -173,6 +175,10 @@ int af3_embed_scatter(void* stream, const int64_t* ids, int n_tok, const void* e
                               frames, post_len, B16M(out), scratch_rows, counts);
 }
 
+int af3_token_step(void* stream, const int64_t* raw_ids, int B, int* unfinished, const int64_t* eos_ids, const int64_t* ctl, int64_t* tok_buf,
+                   int cap, int* gen_idx, int64_t* ids_out, int* done_flags) {
+    return af3::token_step(S(stream), raw_ids, B, unfinished, eos_ids, ctl, tok_buf, cap, gen_idx, ids_out, done_flags);
+}
 size_t af3_argmax_scratch_bytes(int B) { return af3::argmax_scratch_bytes(B); }
 int af3_argmax(void* stream, const float* logits, int B, int V, int64_t* out_ids, void* scratch) {
     return af3::argmax(S(stream), logits, B, V, out_ids, scratch);

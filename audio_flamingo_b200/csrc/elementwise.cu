@@ -752,4 +752,54 @@ int argmax(cudaStream_t stream, const float* logits, int B, int V, int64_t* out,
     return 0;
 }
 
+// One token of the greedy loop's bookkeeping, on the device ([O] GEN:2797-2805): pad rows that have finished, append the token,
+// hand it to the next step's embedding lookup, update the unfinished mask with the EOS set and publish "every row finished".
+// Inside the captured decode step this replaces five small torch launches per token between graph replays.
+//   ctl[0] = number of EOS ids (0: no EOS handling), ctl[1] = pad id;  gen_idx = index of the token being appended (advanced here).
+__global__ void __launch_bounds__(256)
+token_step_kernel(const int64_t* __restrict__ raw_ids, int B, int* __restrict__ unfinished, const int64_t* __restrict__ eos,
+                  const int64_t* __restrict__ ctl, int64_t* __restrict__ tok_buf, int cap, int* __restrict__ gen_idx,
+                  int64_t* __restrict__ ids_out, int* __restrict__ done_flags, unsigned long long* trace) {
+    if (threadIdx.x == 0) trace_mark(trace, 0);
+    pdl_launch_dependents();
+    pdl_wait();
+    if (threadIdx.x == 0) trace_mark(trace, 1);
+    __shared__ int any_unfinished;
+    if (threadIdx.x == 0) any_unfinished = 0;
+    __syncthreads();
+    const int i = *gen_idx;
+    const int n_eos = static_cast<int>(ctl[0]);
+    const int64_t pad = ctl[1];
+    int mine = 0;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        int64_t t = raw_ids[b];
+        int u = 1;
+        if (n_eos > 0) {
+            u = unfinished[b];
+            if (!u) t = pad;                                   // GEN:2797
+            for (int e = 0; e < n_eos; ++e) u = (t == eos[e]) ? 0 : u;   // GEN:2803 (EosTokenCriteria)
+            unfinished[b] = u;
+        }
+        if (i < cap) tok_buf[static_cast<size_t>(b) * cap + i] = t;
+        ids_out[b] = t;
+        mine |= u;
+    }
+    if (mine) any_unfinished = 1;   // benign race: every writer stores 1
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (i < cap) done_flags[i] = (n_eos > 0 && !any_unfinished) ? 1 : 0;   // GEN:2805
+        *gen_idx = i + 1;
+        trace_mark(trace, 3);
+    }
+}
+
+int token_step(cudaStream_t stream, const int64_t* raw_ids, int B, int* unfinished, const int64_t* eos, const int64_t* ctl,
+               int64_t* tok_buf, int cap, int* gen_idx, int64_t* ids_out, int* done_flags) {
+    if (B <= 0) return 0;
+    AF3_REQUIRE(raw_ids && unfinished && eos && ctl && tok_buf && gen_idx && ids_out && done_flags && cap > 0, "token_step: null argument");
+    AF3_CHECK_CUDA(launch_kernel(token_step_kernel, dim3(1), dim3(256), 0, stream, raw_ids, B, unfinished, eos, ctl, tok_buf, cap, gen_idx, ids_out,
+                                 done_flags, trace_next_slot()));
+    return 0;
+}
+
 }  // namespace af3

@@ -768,17 +768,18 @@ class AudioFlamingo3ForConditionalGeneration(nn.Module):
             else:
                 logits = lm.prefill(x, kv_start, cache, logits_to_keep=1).view(B, -1)           # GEN:3724 _prefill
             self._mark("prefill_done")
-            out = torch.empty((B, S + max_new_tokens), device=dev, dtype=torch.int64)
-            out[:, :S] = input_ids.to(dev)
-            eos = unfinished = None
+            eos_list = None
             if eos_token_id is not None:
-                eos = torch.as_tensor([eos_token_id] if isinstance(eos_token_id, int) else list(eos_token_id), device=dev)
+                eos_list = [int(eos_token_id)] if isinstance(eos_token_id, int) else [int(e) for e in eos_token_id]
                 if pad_token_id is None:
-                    pad_token_id = int(eos[0])                                                # GEN: "Setting pad_token_id to eos_token_id"
-                unfinished = torch.ones((B,), device=dev, dtype=torch.int64)
+                    pad_token_id = eos_list[0]                                                # GEN: "Setting pad_token_id to eos_token_id"
             kept_logits = [logits.clone()] if return_logits else None
-            next_ids = ops.argmax(logits)                                                   # GEN:2793
-            result = self._token_loop(step_fn, cache, out, next_ids, logits, kept_logits, eos, unfinished, pad_token_id, S, max_new_tokens)
+            step_fn.begin(ops.argmax(logits), eos_list, pad_token_id)                         # GEN:2793
+            n_done = self._token_loop(step_fn, cache, kept_logits, eos_list is not None, max_new_tokens)
+            out = torch.empty((B, S + n_done), device=dev, dtype=torch.int64)
+            out[:, :S] = input_ids.to(dev)
+            out[:, S:] = step_fn.tok_buf[:, :n_done]
+            result = out
             self._mark("decode_done")
             if return_logits:
                 return result, torch.stack(kept_logits, 1)
@@ -790,37 +791,35 @@ class AudioFlamingo3ForConditionalGeneration(nn.Module):
         """Frees the KV cache and decode graph kept from the last generate() call."""
         self._decode_state = None
 
+    MAX_EOS_IDS = 8      # size of the device-side EOS set (af3_token_step)
     EOS_CHECK_EVERY = 8  # tokens between host reads of the "every row finished" flag (the reference syncs every token)
 
-    def _token_loop(self, step_fn, cache, out, next_ids, logits, kept_logits, eos, unfinished, pad_token_id, S, max_new_tokens):
-        return_logits = kept_logits is not None
+    def _token_loop(self, step_fn, cache, kept_logits, has_eos, max_new_tokens):
+        """Greedy loop ([O] GEN:2743-2809).  The per-token bookkeeping (pad finished rows, append, EOS mask, "all finished") runs on
+        the device inside the decode step (af3_token_step), so one iteration is one graph replay and nothing else; the host reads the
+        "all finished" flags every EOS_CHECK_EVERY tokens (the reference syncs every token).  Returns the number of tokens generated.
+        (Several steps per graph replay were measured too -- 8 per replay: 459.8 vs 456.6 ms for 127 steps, no gain -- and removed.)"""
         n_done = max_new_tokens
-        all_done = []  # per generated token: 0-dim device bool "every row has finished" (read in batches, not per token)
         for i in range(max_new_tokens):
-            if eos is not None:
-                next_ids = next_ids * unfinished + pad_token_id * (1 - unfinished)      # GEN:2797
-            out[:, S + i] = next_ids
-            if eos is not None:
-                unfinished = unfinished & ~torch.isin(next_ids, eos)                    # GEN:2803 (EosTokenCriteria)
-                all_done.append(unfinished.max() == 0)
-                if (i + 1) % self.EOS_CHECK_EVERY == 0 or i + 1 == max_new_tokens:
-                    flags = torch.stack(all_done).cpu()                                 # GEN:2805, one sync per EOS_CHECK_EVERY tokens
-                    if bool(flags.any()):
-                        # tokens enqueued after the stopping step are pads of rows that had all finished: cut them off, the
-                        # result equals the reference's, which stops at exactly that step
-                        n_done = int(flags.nonzero()[0]) + 1
-                        break
             if i + 1 == max_new_tokens:
-                break
-            logits, next_ids = step_fn(next_ids)   # one cached step incl. the greedy argmax (GEN:2793)
-            cache.length += 1
-            if self.stage_host_t is not None:  # bench instrumentation: host time after enqueueing token i + 1
-                self.stage_host_t.append(("tok", time.perf_counter()))
-            if return_logits:
-                kept_logits.append(logits.clone())
-        if return_logits:
+                step_fn.finish()                       # bookkeeping of the last token; no further model step
+            else:
+                logits = step_fn()                     # token i's bookkeeping + one cached step incl. the greedy argmax (GEN:2793)
+                cache.length += 1
+                if self.stage_host_t is not None:      # bench instrumentation: host time after enqueueing token i + 1
+                    self.stage_host_t.append(("tok", time.perf_counter()))
+                if kept_logits is not None:
+                    kept_logits.append(logits.clone())
+            if has_eos and ((i + 1) % self.EOS_CHECK_EVERY == 0 or i + 1 == max_new_tokens):
+                flags = step_fn.done_flags[: i + 1].cpu()                                   # GEN:2805, one sync per EOS_CHECK_EVERY tokens
+                if bool(flags.any()):
+                    # tokens enqueued after the stopping step are pads of rows that had all finished: cut them off, the result
+                    # equals the reference's, which stops at exactly that step
+                    n_done = int(flags.nonzero()[0]) + 1
+                    break
+        if kept_logits is not None:
             del kept_logits[n_done:]
-        return out[:, : S + n_done]
+        return n_done
 
     def _decode_runner(self, B, cache, use_graph):
         """Returns step(next_ids[int64 B]) -> (fp32 logits [B, V], greedy ids [B]).  With use_graph the whole step (embedding
@@ -829,51 +828,93 @@ class AudioFlamingo3ForConditionalGeneration(nn.Module):
         dev = lm.lm_head.weight.device
         table = lm.model.embed_tokens.weight
         scratch = ops.decode_attention_scratch(B, lm.H, lm.D, cache.Tmax, dev)
-        ids_buf = torch.zeros((B,), device=dev, dtype=torch.int64)
+        # device-side state of the greedy loop (addresses baked into the captured graph; contents set per generate() call)
+        cap = cache.Tmax
+        raw_ids = torch.zeros((B,), device=dev, dtype=torch.int64)      # argmax of the previous logits
+        ids_buf = torch.zeros((B,), device=dev, dtype=torch.int64)      # token fed to the next step
+        unfinished = torch.ones((B,), device=dev, dtype=torch.int32)
+        eos_dev = torch.zeros((self.MAX_EOS_IDS,), device=dev, dtype=torch.int64)
+        ctl = torch.zeros((2,), device=dev, dtype=torch.int64)          # {number of EOS ids, pad id}
+        tok_buf = torch.zeros((B, cap), device=dev, dtype=torch.int64)
+        gen_idx = torch.zeros((1,), device=dev, dtype=torch.int32)
+        done_flags = torch.zeros((cap,), device=dev, dtype=torch.int32)
+        am_out = raw_ids
 
         use_pdl = os.environ.get("AF3_PDL", "1") != "0"
 
-        def eager(next_ids):
+        def bookkeeping():
+            ops.token_step(raw_ids, unfinished, eos_dev, ctl, tok_buf, gen_idx, ids_buf, done_flags)
+
+        def eager():
             # programmatic dependent launch along the whole step: each kernel's prologue and the GEMMs' weight
             # prefetch overlap the tail of the kernel before it (the kernels order their dependent accesses themselves)
             _lib.load().af3_set_pdl(1 if use_pdl else 0)
             phase, ops.PHASE = ops.PHASE, "decode"
             try:
-                x, _ = ops.embed_scatter(next_ids, table, -1, None, 0, 1, None)
+                bookkeeping()
+                x, _ = ops.embed_scatter(ids_buf, table, -1, None, 0, 1, None)
                 logits = lm.decode_step(x, cache, scratch)
-                return logits, ops.argmax(logits)
+                ops.argmax(logits, out=am_out)
+                return logits
             finally:
                 ops.PHASE = phase
                 _lib.load().af3_set_pdl(0)
 
-        if not use_graph:
-            return eager
         state = {"graph": None, "out": None, "warm": 0}
 
-        def step(next_ids):
-            ids_buf.copy_(next_ids)
-            if state["graph"] is None:
-                if state["warm"] < 1:  # first step eagerly (configures kernels, warms the allocator)
-                    state["warm"] += 1
-                    return eager(ids_buf)
-                g = torch.cuda.CUDAGraph()
-                torch.cuda.synchronize()
-                prof, ops.PROFILE = ops.PROFILE, None  # timing events cannot be recorded inside a capture
-                n0 = ops.LAUNCHES
-                t0 = len(ops.TRACE_LOG) if ops.TRACE_LOG is not None else 0
-                with torch.cuda.graph(g):
-                    state["out"] = eager(ids_buf)
-                if ops.TRACE_LOG is not None:  # timeline tool: which trace-log entries are the captured step's launches
-                    ops.TRACE_LOG.append(("graph_capture", t0, len(ops.TRACE_LOG)))
-                state["launches"] = ops.LAUNCHES - n0
-                ops.LAUNCHES = n0  # capture launched nothing; replays are counted below
-                ops.PROFILE = prof
-                state["graph"] = g
-            state["graph"].replay()  # (capture does not execute: the first replay runs this token's step)
-            ops._count(state["launches"])
-            return state["out"]
+        class Step:
+            """step() -> fp32 logits [B, V] of the next token: device-side bookkeeping of the current token, embedding gather, 28
+            layers, head, argmax -- captured once in a CUDA graph when use_graph and replayed; positions advance on the device."""
 
-        return step
+            def begin(self_, first_ids, eos_list, pad_token_id):
+                if eos_list is not None and len(eos_list) > self.MAX_EOS_IDS:
+                    raise AF3Error(f"at most {self.MAX_EOS_IDS} eos_token_id values are supported")
+                raw_ids.copy_(first_ids)
+                unfinished.fill_(1)
+                gen_idx.zero_()
+                done_flags.zero_()
+                n_eos = len(eos_list) if eos_list is not None else 0
+                # scalar fills, not host-to-device copies: a copy from pageable memory would block the host until the queued
+                # encoder + prefill work has drained (measured: 340 ms of lost run-ahead per generate() call)
+                ctl[0:1].fill_(n_eos)
+                ctl[1:2].fill_(int(pad_token_id) if pad_token_id is not None else 0)
+                for j in range(n_eos):
+                    eos_dev[j:j + 1].fill_(int(eos_list[j]))
+
+            def finish(self_):
+                phase, ops.PHASE = ops.PHASE, "decode"
+                try:
+                    bookkeeping()
+                finally:
+                    ops.PHASE = phase
+
+            def __call__(self_):
+                if not use_graph:
+                    return eager()
+                if state["graph"] is None:
+                    if state["warm"] < 1:  # first step eagerly (configures kernels, warms the allocator)
+                        state["warm"] += 1
+                        return eager()
+                    g = torch.cuda.CUDAGraph()
+                    torch.cuda.synchronize()
+                    prof, ops.PROFILE = ops.PROFILE, None  # timing events cannot be recorded inside a capture
+                    n0 = ops.LAUNCHES
+                    t0 = len(ops.TRACE_LOG) if ops.TRACE_LOG is not None else 0
+                    with torch.cuda.graph(g):
+                        state["out"] = eager()
+                    if ops.TRACE_LOG is not None:  # timeline tool: which trace-log entries are the captured step's launches
+                        ops.TRACE_LOG.append(("graph_capture", t0, len(ops.TRACE_LOG)))
+                    state["launches"] = ops.LAUNCHES - n0
+                    ops.LAUNCHES = n0  # capture launched nothing; replays are counted below
+                    ops.PROFILE = prof
+                    state["graph"] = g
+                state["graph"].replay()  # (capture does not execute: the first replay runs this token's step)
+                ops._count(state["launches"])
+                return state["out"]
+
+        st = Step()
+        st.tok_buf, st.done_flags = tok_buf, done_flags
+        return st
 
 
 class MusicFlamingoForConditionalGeneration(AudioFlamingo3ForConditionalGeneration):

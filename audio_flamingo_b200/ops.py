@@ -398,6 +398,17 @@ def embed_scatter(ids, table, audio_token_id, audio_embeds, n_win, frames, post_
     return out, counts
 
 
+def token_step(raw_ids, unfinished, eos_ids, ctl, tok_buf, gen_idx, ids_out, done_flags):
+    """Device-side bookkeeping of one greedy token (include/af3b200.h af3_token_step)."""
+    lib = _lib.load()
+    _req(raw_ids, torch.int64, "raw_ids"), _req(tok_buf, torch.int64, "tok_buf"), _req(unfinished, torch.int32, "unfinished")
+    B, cap = tok_buf.shape
+    with _Timed(("token_step", B, cap, 0, 0)):
+        check(lib.af3_token_step(stream_ptr(), ptr(raw_ids), B, ptr(unfinished), ptr(eos_ids), ptr(ctl), ptr(tok_buf), cap, ptr(gen_idx),
+                                 ptr(ids_out), ptr(done_flags)), "af3_token_step")
+    _count(1)
+
+
 def argmax(logits, out=None):
     lib = _lib.load()
     _req(logits, torch.float32, "logits")

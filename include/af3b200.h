@@ -189,6 +189,15 @@ int af3_embed_scatter(void* stream, const int64_t* ids, int n_tok, const void* e
 size_t af3_argmax_scratch_bytes(int B);
 int af3_argmax(void* stream, const float* logits, int B, int V, int64_t* out_ids, void* scratch);
 
+/* [O] generation/utils.py:2797-2805 (_sample, greedy): per generated token -- rows that have finished emit pad_token_id, the
+ * token is appended, the unfinished mask is updated with the EOS set (EosTokenCriteria) and "every row finished" is published.
+ * Device-side, so the whole token fits in the captured decode step.  raw_ids [B] (the argmax of the previous logits),
+ * unfinished [B] (1 = running; updated), eos_ids [ctl[0]] ids, ctl = {number of EOS ids (0: no EOS handling), pad id},
+ * tok_buf [B][cap] receives column *gen_idx, *gen_idx is advanced, ids_out [B] = the tokens fed to the next step,
+ * done_flags[*gen_idx] = 1 iff EOS handling is on and no row is unfinished.  (ABI v3) */
+int af3_token_step(void* stream, const int64_t* raw_ids, int B, int* unfinished, const int64_t* eos_ids, const int64_t* ctl, int64_t* tok_buf,
+                   int cap, int* gen_idx, int64_t* ids_out, int* done_flags);
+
 #ifdef __cplusplus
 }
 #endif

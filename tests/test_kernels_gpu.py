@@ -495,3 +495,36 @@ def test_fused_rmsnorm_across_few_token_gemms(ops, B, K, N, mode):
     tol = 2 ** -7 * unf.float().abs() + 2e-2
     assert int((d > tol).sum()) == 0, f"max diff {d.max().item()}"
     assert (d > 0).float().mean().item() < 0.05, "fused and unfused should agree bit for bit almost everywhere"
+
+
+def test_token_step_is_the_references_per_token_rule(ops):
+    """af3_token_step against the reference's lines restated with torch ops ([O] GEN:2797-2805): finished rows emit pad, the token is
+    appended, the unfinished mask is updated with the EOS set, "every row finished" is published -- over several consecutive tokens,
+    with and without EOS handling, B above one thread block's width."""
+    for B, n_eos in ((5, 1), (300, 2), (64, 0)):
+        g = torch.Generator(device="cpu").manual_seed(B)
+        cap, steps, pad = 16, 6, 7
+        eos = torch.tensor([3, 11][:max(n_eos, 1)], dtype=torch.int64).cuda()
+        eos_dev = torch.zeros((8,), dtype=torch.int64, device="cuda")
+        eos_dev[: eos.numel()] = eos
+        ctl = torch.tensor([n_eos, pad], dtype=torch.int64).cuda()
+        unfinished = torch.ones((B,), dtype=torch.int32, device="cuda")
+        tok_buf = torch.full((B, cap), -1, dtype=torch.int64, device="cuda")
+        gen_idx = torch.zeros((1,), dtype=torch.int32, device="cuda")
+        ids_out = torch.zeros((B,), dtype=torch.int64, device="cuda")
+        flags = torch.full((cap,), -1, dtype=torch.int32, device="cuda")
+        ref_unf = torch.ones((B,), dtype=torch.int64)
+        for i in range(steps):
+            raw = torch.randint(0, 14 if i < steps - 1 else 4, (B,), generator=g, dtype=torch.int64)
+            if i == steps - 1 and n_eos:
+                raw[:] = 3   # everybody finishes on the last token at the latest
+            ops.token_step(raw.cuda(), unfinished, eos_dev, ctl, tok_buf, gen_idx, ids_out, flags)
+            nxt = raw.clone()
+            if n_eos:
+                nxt = nxt * ref_unf + pad * (1 - ref_unf)                                # GEN:2797
+                ref_unf = ref_unf & ~torch.isin(nxt, eos.cpu())                          # GEN:2803
+            assert torch.equal(tok_buf[:, i].cpu(), nxt) and torch.equal(ids_out.cpu(), nxt)
+            assert int(flags[i]) == (1 if (n_eos and int(ref_unf.max()) == 0) else 0)    # GEN:2805
+            if n_eos:
+                assert torch.equal(unfinished.cpu().long(), ref_unf)
+        assert int(gen_idx) == steps and (tok_buf[:, steps:] == -1).all() and (flags[steps:] == -1).all()
