@@ -278,3 +278,110 @@ def test_packing_leaves_one_copy_of_the_decoder_projections():
     with torch.no_grad():
         l0.mlp.gate_proj.weight[3, 5] = 7.0          # an in-place parameter update is what the kernels read
     assert float(wgu[3, 5]) == 7.0
+
+
+class _FakeStep:
+    """Stands in for the decode runner's step object: counts calls and raises the device-side "all finished" flag at a chosen token."""
+
+    def __init__(self, all_done_at, cap=64):
+        self.done_flags = torch.zeros((cap,), dtype=torch.int32)
+        self.all_done_at, self.tokens, self.model_steps, self.finished = all_done_at, 0, 0, 0
+
+    def _bookkeeping(self):
+        if self.all_done_at is not None and self.tokens >= self.all_done_at:
+            self.done_flags[self.tokens] = 1
+        self.tokens += 1
+
+    def __call__(self):
+        self._bookkeeping()
+        self.model_steps += 1
+        return torch.zeros((1, 4))
+
+    def finish(self):
+        self._bookkeeping()
+        self.finished += 1
+
+
+@pytest.mark.parametrize("max_new,all_done_at,has_eos,expect_tokens,expect_model_steps", [
+    (5, None, False, 5, 4),      # no EOS handling: max_new tokens, max_new - 1 cached steps, the last token only gets its bookkeeping
+    (1, None, True, 1, 0),       # a single new token never runs a cached step
+    (20, 2, True, 3, 8),         # every row finished at token index 2: 3 tokens returned; the flags are read after 8 tokens
+    (20, 7, True, 8, 8),         # finished exactly at a check boundary
+    (20, 8, True, 9, 16),        # ... one token later: seen at the next check
+    (12, 11, True, 12, 11),      # finished on the very last token
+    (12, None, True, 12, 11),    # EOS handling on, nobody finishes
+])
+def test_token_loop_counts_and_eos_cut(max_new, all_done_at, has_eos, expect_tokens, expect_model_steps):
+    """modeling._token_loop on a fake step object: how many tokens are returned, how many cached steps are enqueued, that the last
+    token goes through finish() (no model step after it), and that the cached-length bookkeeping follows the enqueued steps."""
+    import types
+
+    from audio_flamingo_b200.modeling import AudioFlamingo3ForConditionalGeneration as M
+
+    me = types.SimpleNamespace(EOS_CHECK_EVERY=M.EOS_CHECK_EVERY, stage_host_t=None)
+    cache = types.SimpleNamespace(length=100)
+    step = _FakeStep(all_done_at)
+    kept = []
+    n = M._token_loop(me, step, cache, kept, has_eos, max_new)
+    assert n == expect_tokens
+    assert step.model_steps == expect_model_steps and cache.length == 100 + expect_model_steps
+    assert step.finished == (1 if step.tokens == max_new else 0)
+    assert len(kept) <= n   # logits kept per returned token at most (the caller seeds the list with the prefill logits)
+
+
+def test_trace_records_slots_and_per_cta_tails():
+    """trace.DecodeTrace.graph_launches on a hand-made stamp buffer: slots add up to the step, stream / tail split at the last
+    accumulator, per-CTA "accumulator -> exit" statistics (what separates publishing a split-K partial from reducing)."""
+    from audio_flamingo_b200 import trace as T
+
+    tr = T.DecodeTrace(torch.device("cpu"), n_slots=4)
+    raw = tr.buf.view(4, -1, 4)
+    t0 = 1_000_000
+    # launch 0 ("rmsnorm", 2 CTAs): entry, dependency resolved, -, exit
+    raw[0, 0] = torch.tensor([t0 + 0, t0 + 1000, 0, t0 + 3000])
+    raw[0, 1] = torch.tensor([t0 + 100, t0 + 1000, 0, t0 + 3100])
+    # launch 1 (few-token GEMM, 3 CTAs): two publish a partial (1.5 us after their accumulator), one reduces (6 us)
+    raw[1, 0] = torch.tensor([t0 + 2000, t0 + 4000, t0 + 9000, t0 + 10500])
+    raw[1, 1] = torch.tensor([t0 + 2100, t0 + 4100, t0 + 9500, t0 + 11000])
+    raw[1, 2] = torch.tensor([t0 + 2200, t0 + 4000, t0 + 10000, t0 + 16000])
+    tr.log = [(("rmsnorm", 32, 3584, 0, 0, "decode"), 0, 1), (("gemm", 32, 3584, 3584, 4, "decode"), 1, 2), ("graph_capture", 0, 2)]
+    L = tr.graph_launches()
+    assert [r["kind"] for r in L] == ["rmsnorm", "gemm 3584x3584"]
+    assert L[0]["slot_us"] == pytest.approx(3.1) and L[1]["slot_us"] == pytest.approx(16.0 - 3.1)
+    assert sum(r["slot_us"] for r in L) == pytest.approx(16.0)          # the slots add up to the step
+    assert L[1]["gap_us"] == pytest.approx(4.0 - 3.1) and L[1]["lead_us"] == pytest.approx(2.0)
+    assert L[1]["stream_us"] == pytest.approx(6.0) and L[1]["tail_us"] == pytest.approx(6.0)
+    assert L[1]["cta_tail_us"]["min"] == pytest.approx(1.5) and L[1]["cta_tail_us"]["max"] == pytest.approx(6.0)
+    assert L[1]["mid_spread_us"] == pytest.approx(1.0)
+    agg = T.DecodeTrace.aggregate(L)
+    assert agg["gemm 3584x3584"]["n"] == 1
+
+
+def test_launch_shares_weights_decode_kernels(tmp_path):
+    """profiles/launch_shares.py: the few-token GEMMs, decode attention and row-block RMSNorm of the profiled eager decode steps are
+    weighted up to the 127 cached steps of the workload, prefill kernels are not (ncu prints template arguments with or without
+    the "(int)" casts depending on the version)."""
+    import subprocess
+    import sys
+
+    hdr = '"ID","Process ID","Process Name","Host Name","Kernel Name","Context","Stream","Block Size","Grid Size","Device","CC","Section Name","Metric Name","Metric Unit","Metric Value"'
+    def row(i, name, ns):
+        return f'"{i}","1","python","h","{name}","1","7","(1, 1, 1)","(1, 1, 1)","0","10.0","s","gpu__time_duration.sum","ns","{ns}"'
+    names = [("void af3::gemm_kernel<256, 1, 4, 0, 8, 4, 0>(CUtensorMap_st, int)", 4_000_000),
+             ("void af3::gemm_kernel<32, 2, 6, 1, 8, 4, 0>(CUtensorMap_st, int)", 50_000),
+             ("void af3::gemm_kernel<(int)32, (int)1, (int)10, (bool)1, (int)4, (int)4, (bool)0>(CUtensorMap_st, int)", 30_000),
+             ("void af3::decode_attn_kernel<8, 3>(CUtensorMap_st, int)", 18_000),
+             ("af3::rope_table_kernel(float *)", 2_000)]
+    src = tmp_path / "launches.csv"
+    src.write_text("==PROF== noise\n" + hdr + "\n" + "\n".join(row(i, n, v) for i, (n, v) in enumerate(names)) + "\n")
+    dst = tmp_path / "shares.md"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run([sys.executable, os.path.join(root, "profiles", "launch_shares.py"), str(src), str(dst)], check=True, capture_output=True)
+    lines = [l for l in dst.read_text().splitlines() if l.startswith("| ") and "`" in l]
+    by = {l.split("`")[1]: l.split("|") for l in lines}
+    w = 127.0   # one profiled decode step (one rope_table launch) -> x 127
+    assert by["void af3::gemm_kernel<32, 2, 6, 1, 8, 4, 0>"][1].strip() == f"{50_000 * w / 1e6:.2f}" and by["void af3::gemm_kernel<32, 2, 6, 1, 8, 4, 0>"][4].strip() == "yes"
+    k = [x for x in by if x.startswith("void af3::gemm_kernel<(int)32")][0]
+    assert by[k][4].strip() == "yes"
+    assert by["void af3::gemm_kernel<256, 1, 4, 0, 8, 4, 0>"][1].strip() == "4.00" and by["void af3::gemm_kernel<256, 1, 4, 0, 8, 4, 0>"][4].strip() == ""
+    assert by["void af3::decode_attn_kernel<8, 3>"][4].strip() == "yes"
