@@ -9,10 +9,11 @@
 // output dims are the UMMA M dimension and the (padded) 16 query heads are N:
 //     S^T[key, head] = K_tile[key, :] . Q[head, :]          tcgen05.mma 128x16x16 x 8,  A = K tile (K-major, via TMA)
 //     O^T[dim, head] = V_tile^T[dim, key] . P^T[key, head]   tcgen05.mma 128x16x16 x 8,  A = V tile read MN-major
-// so K and V never pass through registers.  Roles: warps 0-3 softmax + accumulation (thread = key lane for S, = output
-// dim lane for O; the heads are split between two warp groups, see below), warp 8 issues the MMAs, warp 9 the TMA loads.  S, P and the per-chunk O are double-buffered so that
-// S_{i+1} = K_{i+1} Q^T and the loads run ahead of softmax_i, and O_i is folded into the register accumulator after
-// softmax_{i+1} has been handed to the tensor core (the chunk's P.V product is then long complete).
+// so K and V never pass through registers.  Roles: warps 0-7 softmax + accumulation (thread = key lane for S, = output dim lane
+// for O; the heads are split between two warp groups, see the kernel), warp 8 issues the MMAs, warp 9 the TMA loads.  S, P and
+// the per-chunk O are double-buffered so that S_{i+1} = K_{i+1} Q^T and the loads run ahead of softmax_i, and O_i is folded into
+// the register accumulator after softmax_{i+1} has been handed to the tensor core (the chunk's P.V product is then long complete).
+// Measured (round 2): the K/V ring runs far ahead; what bounds the kernel is the softmax warps' serial chain per chunk (~2 us).
 // Splits: the host picks nz = min(chunks(Tmax), SMs / (B*Hkv)) so that B*Hkv*nz CTAs (one per SM, 207 KB of smem) cover
 // the GPU; the live chunk range [start/128, ceil(ctx/128)) of each sequence is divided evenly over the nz splits at run
 // time.  nz == 1 (config 2: 32 x 4 = 128 CTAs) writes the normalised output directly; otherwise every split writes an
