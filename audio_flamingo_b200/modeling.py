@@ -822,8 +822,10 @@ class AudioFlamingo3ForConditionalGeneration(nn.Module):
         return n_done
 
     def _decode_runner(self, B, cache, use_graph):
-        """Returns step(next_ids[int64 B]) -> (fp32 logits [B, V], greedy ids [B]).  With use_graph the whole step (embedding
-        gather, 28 layers, head, argmax) is captured once in a CUDA graph and replayed; positions advance on the device."""
+        """Returns the step object of the greedy loop: begin(first_ids, eos_list, pad) arms the device-side state, step() enqueues one
+        token (bookkeeping, embedding gather, 28 layers, head, argmax) and returns the fp32 logits [B, V] buffer of the next token,
+        finish() enqueues the bookkeeping of the last token; tok_buf [B, cap] / done_flags [cap] receive the tokens and the "every
+        row finished" flags.  With use_graph the step is captured once in a CUDA graph and replayed; positions advance on the device."""
         lm = self.language_model
         dev = lm.lm_head.weight.device
         table = lm.model.embed_tokens.weight
